@@ -1,0 +1,175 @@
+/*
+ * include/prt_b200.h -- C ABI of libprt_b200.so, the B200 (sm_100a) engine behind the reference's
+ * Python plugin surface.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * The reference (ReaganCardoza/Physics-Based-Ray-Tracing) has no native interface of its own: its hot
+ * path calls Mitsuba 3's Python API.  Each entry point below names the reference call site it replaces
+ * (file:line under /root/reference).  INTEGRATION.md shows the ctypes stubs a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative prt_status otherwise; prt_last_error() gives text
+ *   - arrays without a `_dev` suffix are caller-owned contiguous HOST buffers; `_dev` are device pointers
+ *     on the context's device (e.g. torch tensors' data_ptr()), `stream` is a cudaStream_t (0 = default)
+ *   - matrices are row-major 4x4 float64 (converted to fp32 on upload, as Mitsuba's llvm_ad_* `Float`)
+ *   - one context per (process, device); calls on one context are serialised by an internal mutex
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with PRT_ERR_CUDA
+ */
+#ifndef PRT_B200_H
+#define PRT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PRT_OK = 0,
+    PRT_ERR_INVALID = -1,   /* bad argument / handle                       */
+    PRT_ERR_CUDA = -2,      /* CUDA runtime error (see prt_last_error)     */
+    PRT_ERR_STATE = -3,     /* e.g. tracing an uncommitted scene           */
+    PRT_ERR_UNSUPPORTED = -4
+} prt_status;
+
+/* analytic primitives, object-space definitions (Mitsuba conventions) */
+enum { PRT_SPHERE = 0, PRT_RECTANGLE = 1, PRT_CONE = 2, PRT_DISK = 3, PRT_CYLINDER = 4 };
+/* materials */
+enum { PRT_MAT_ULTRA = 0, PRT_MAT_DIFFUSE = 1, PRT_MAT_DIELECTRIC = 2, PRT_MAT_CONDUCTOR = 3, PRT_MAT_NULL = 4 };
+/* quirk switches of the acquisition loop; 0 = canonical (Appendix F) */
+enum {
+    PRT_QF_CLAMP_TIDX = 1u << 0,        /* CustomIntegrator.py:192   clamp instead of drop            */
+    PRT_QF_TOF_LAST_SEGMENT = 1u << 1,  /* CustomIntegrator.py:165   tof never advances                */
+    PRT_QF_SINGLE_BOUNCE = 1u << 2,     /* CustomIntegrator.py:365-376 as written: one bounce per ray  */
+    PRT_QF_RR_NO_ABS = 1u << 3,         /* CustomIntegrator.py:220   rr prob without abs               */
+    PRT_QF_CONNECT_TO_TARGET = 1u << 4  /* not the reference: connection ray ends at the element      */
+};
+
+typedef struct prt_context prt_context;
+typedef struct prt_scene prt_scene;
+
+/* ---- context ------------------------------------------------------------------------------- */
+const char *prt_last_error(void);                 /* thread-local message of the last failure    */
+const char *prt_version(void);
+int prt_device_count(int *count);
+/* replaces mi.set_variant("cuda_ad_mono") (TestScene.py:3): binds a CUDA device */
+int prt_create(int device, prt_context **out);
+int prt_destroy(prt_context *);
+int prt_device_info(prt_context *, int *sm_count, int *cc_major, int *cc_minor, uint64_t *global_mem_bytes);
+
+/* ---- scene upload (replaces mi.load_dict / mi.load_file, USMain.py:257; Mitsuba builds Embree here) */
+int prt_scene_create(prt_context *, prt_scene **out);
+int prt_scene_destroy(prt_scene *);
+/* kind = PRT_MAT_*; p[8]: ULTRA {impedance, roughness} (CustomBSDF.py:12-18), DIFFUSE {r,g,b},
+ * DIELECTRIC {int_ior, ext_ior}, CONDUCTOR {r,g,b}; emission = area-emitter radiance or NULL */
+int prt_scene_add_material(prt_scene *, int kind, const double p[8], const double emission_rgb[3], int *material_id);
+/* mi.traverse(scene)[...] = v ; params.update()  (USMain.py:259,264-265): no rebuild */
+int prt_scene_set_material_param(prt_scene *, int material_id, int index, double value);
+int prt_scene_add_primitive(prt_scene *, int kind, const double to_world[16], int material_id, int flip_normals,
+                            int *shape_id);
+/* v [nv][3], vn [nv][3] or NULL, idx [nt][3] (object space) */
+int prt_scene_add_mesh(prt_scene *, const double *v, uint32_t nv, const double *vn, const uint32_t *idx, uint32_t nt,
+                       const double to_world[16], int material_id, int flip_normals, int *shape_id);
+
+typedef struct {
+    uint32_t n_primitives, n_triangles, n_nodes, max_leaf_size;
+    float    build_ms;          /* Morton + sort + hierarchy + refit, CUDA-event timed */
+    float    sah_cost;          /* SAH cost of the final tree (root area normalised)   */
+    float    scene_lo[3], scene_hi[3];
+    uint64_t device_bytes;      /* bytes of device memory held by the scene            */
+} prt_bvh_stats;
+/* SoA upload + GPU LBVH build (Morton codes -> radix sort -> Karras hierarchy -> bottom-up refit) */
+int prt_scene_commit(prt_scene *, prt_bvh_stats *out /* nullable */);
+
+/* ---- ray queries == scene.ray_intersect(ray) (CustomIntegrator.py:146,159,309,324) ------------ */
+/* o,d [n][3] f32, tmax [n] or NULL (= inf).  Outputs nullable.  prim = -1, t = inf on a miss.
+ * prim: analytic primitives first [0, n_primitives), then n_primitives + triangle index (input order) */
+int prt_trace_closest(prt_scene *, const float *o, const float *d, const float *tmax, uint64_t n,
+                      float *t, int32_t *prim, int32_t *shape, float *p /*[n][3]*/, float *ng, float *ns, float *wi,
+                      float *sh_s /*[n][3] shading-frame tangent s; t = n x s*/);
+int prt_trace_occluded(prt_scene *, const float *o, const float *d, const float *tmax, uint64_t n, uint8_t *hit);
+/* == UltraBSDF.sample(ctx, si, sample1, sample2) (CustomBSDF.py:87-175) on n explicit interactions */
+int prt_ultra_bsdf_sample(prt_context *, uint64_t n, const float *wi, const float *ng, const float *ns,
+                          const float *impedance, const float *roughness, const float *s1, const float *s2,
+                          float *dir /*[n][3]*/, float *pdf, float *amp, int32_t *reflect);
+
+/* ---- acquisition == UltraIntegrator.simulate_acquisition{,_parallel}(scene) --------------------
+ * (CustomIntegrator.py:60-232, 235-405).  Property names / defaults: CustomIntegrator.py:16-42. */
+typedef struct {
+    int32_t  n_angles, n_elements, time_samples, max_depth;
+    double   pitch, fs, sound_speed, frequency, attenuation;
+    double   main_beam_deg, cutoff_deg, max_path_len;   /* max_path_len = 0.2 (CustomIntegrator.py:141) */
+    double   sensor_to_world[16];                        /* UltraSensor.transform                         */
+    uint32_t quirk_flags;
+    uint32_t _pad;
+    const double *angles_deg;                            /* [n_angles], host                              */
+} prt_acq_params;
+
+typedef struct {
+    uint64_t paths, segments, rays, deposits, misses;
+    float    kernel_ms;     /* device time of the path kernel (CUDA events)   */
+    float    total_ms;      /* including zero-fill and copies                 */
+    uint32_t launches;      /* kernels launched by this call                  */
+    uint32_t _pad;
+} prt_acq_stats;
+
+/* Traces samples s = sample_offset + j*sample_stride < spp_total of every (angle, element).
+ * Path (a, e, s) draws from PCG32 seeded by sample_tea_32(seed, (a*n_e + e)*spp_total + s).
+ * channel_buf [n_a][n_e][T] f32 is OVERWRITTEN with this call's deposits (each scaled by 1/spp_total);
+ * tx_delays [n_a][n_e] f32 = x_e sin(theta_a)/c  (CustomIntegrator.py:87,254-257). */
+int prt_acquire(prt_scene *, const prt_acq_params *, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                uint32_t sample_stride, float *channel_buf, float *tx_delays, prt_acq_stats *stats /*nullable*/);
+/* Same, accumulating (+=) into a caller-owned DEVICE buffer on `stream`; asynchronous.  stats_dev:
+ * 5 x uint64 {paths, segments, rays, deposits, misses} accumulated with atomics, or NULL. */
+int prt_acquire_dev(prt_scene *, const prt_acq_params *, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                    uint32_t sample_stride, float *channel_buf_dev, float *tx_delays_dev, uint64_t *stats_dev,
+                    void *stream);
+
+/* decision-level trace of selected paths (parity tests): rec [n][max_depth] */
+typedef struct {
+    int32_t valid, prim, shape, recv, visible, reflect, k, survive;
+    float   t, total_time, press, amp, atten, dir[3];
+} prt_seg_record;
+int prt_acquire_trace(prt_scene *, const prt_acq_params *, uint64_t seed, uint32_t spp_total,
+                      const uint64_t *path_idx, uint64_t n, prt_seg_record *rec);
+
+/* ---- light-transport path tracer == mi.render(scene) with the `path` integrator that
+ * scenes/cbox.xml:5-9 names (max_depth, rr_depth 5), perspective sensor (:11-21), independent
+ * sampler (:22-24), hdrfilm + tent filter (:25-31).  Mitsuba semantics: SURVEY.md Appendix C.7. */
+typedef struct {
+    double   to_world[16];
+    double   fov_deg;            /* along the SMALLER image axis (cbox.xml:12) */
+    double   near_clip, far_clip;
+    int32_t  width, height;
+    int32_t  max_depth, rr_depth;
+    int32_t  rfilter;            /* 0 = box, 1 = tent (radius 1) */
+    int32_t  _pad;
+} prt_render_params;
+
+typedef struct {
+    uint64_t paths, segments, rays, shadow_rays;
+    float    kernel_ms, total_ms;
+    uint32_t launches, _pad;
+} prt_render_stats;
+
+/* film_rgbw [H][W][4] f32 = (sum w*R, sum w*G, sum w*B, sum w), OVERWRITTEN.  Sample s of pixel (x,y)
+ * uses PCG32 stream sample_tea_32(seed, (y*W + x)*spp_total + s) (64-bit index folded as documented). */
+int prt_render_path(prt_scene *, const prt_render_params *, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                    uint32_t sample_stride, float *film_rgbw, prt_render_stats *stats /*nullable*/);
+int prt_render_path_dev(prt_scene *, const prt_render_params *, uint64_t seed, uint32_t spp_total,
+                        uint32_t sample_offset, uint32_t sample_stride, float *film_rgbw_dev, uint64_t *stats_dev,
+                        void *stream);
+
+/* ---- "next" row f1: delay-and-sum beamformer + envelope (replaces ultraspy, USMain.py:129-208) -- */
+typedef struct {
+    int32_t n_angles, n_elements, time_samples, nx, nz;
+    double  fs, sound_speed, pitch, t0;
+    double  f_number;            /* 0 = full aperture */
+} prt_das_params;
+/* channel [n_a][n_e][T], tx_delays [n_a][n_e], angles_deg [n_a], x [nx], z [nz] -> rf [nx][nz] f32 and
+ * envelope [nx][nz] f32 (magnitude of the analytic signal along z) */
+int prt_das_beamform(prt_context *, const prt_das_params *, const float *channel, const float *tx_delays,
+                     const double *angles_deg, const float *x, const float *z, float *rf, float *envelope);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

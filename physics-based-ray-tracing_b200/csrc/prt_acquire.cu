@@ -1,0 +1,364 @@
+// prt_acquire.cu -- the acquisition hot path as one persistent sm_100a kernel.
+//
+// Replaces UltraIntegrator.simulate_acquisition (/root/reference/CustomIntegrator.py:60-232, one width-1
+// Dr.Jit while_loop per ray) and simulate_acquisition_parallel (:235-405, GIL-bound thread pool).
+// One CUDA thread owns one path at a time and keeps its whole state in registers (ray, amp, atten, tof,
+// path length, PCG32 stream); when a path ends the lane immediately regenerates the next path of its
+// strided list, so warps stay full until the tail.  Lanes of a warp work on consecutive (angle, element)
+// pairs: nearly parallel primary rays (coherent traversal) whose deposits land in different
+// channel_buf rows (no same-address atomic storms).  Analytic primitives are staged in shared memory;
+// deposits are fire-and-forget red.global.add.f32 into the L2-resident channel buffer.
+// Canonical path semantics: SURVEY.md Appendix F.  Line tags CI:n / CB:n cite the reference files.
+#include <cmath>
+
+#include "prt_internal.h"
+
+namespace prt {
+
+static constexpr int ACQ_THREADS = 256;
+static constexpr int MAX_SMEM_PRIMS = 64;
+
+struct AcqDev {
+    DScene sc;
+    float4 T0, T1, T2;  // sensor to_world rows
+    float3 nT;          // normalize(T * (0,0,1))
+    float c, fs, pitch, two_pi_f, att_k, alpha_m, alpha_c, cos_c, max_len, n_rays, inv_spp;
+    int n_a, n_e, Tn, max_depth;
+    unsigned qf;
+    const float2 *sincos;  // [n_a] (sin theta, cos theta)
+    uint64_t seed;
+    uint32_t spp_total, s_offset, s_stride;
+    uint64_t n_s, total;   // samples per (a,e) for this call, total paths of this call
+    float *buf, *tx;
+    unsigned long long *stats;  // {paths, segments, rays, deposits, misses}
+};
+
+struct PathState {
+    float3 o, d;
+    float amp, atten, tof, geo, t0;
+    int a, depth;
+    Pcg32 rng;
+};
+
+__device__ __forceinline__ float elem_x(const AcqDev &P, int e) { return P.pitch * ((float) e - (float) (P.n_e - 1) * 0.5f); }  // CI:84
+
+__device__ __forceinline__ void init_path(const AcqDev &P, uint64_t ae, uint32_t s, PathState &ps) {
+    int a = (int) (ae / (uint64_t) P.n_e), e = (int) (ae % (uint64_t) P.n_e);
+    float2 sc = __ldg(P.sincos + a);
+    float xe = elem_x(P, e);
+    ps.t0 = (xe * sc.x) / P.c;                                                  // CI:87
+    ps.o = xpoint(P.T0, P.T1, P.T2, mk3(xe, 0.0f, 0.0f));                       // CI:97,103
+    ps.d = normalize(xvec(P.T0, P.T1, P.T2, mk3(sc.x, 0.0f, sc.y)));            // CI:98,104
+    ps.amp = 1.0f; ps.atten = 1.0f; ps.tof = 0.0f; ps.geo = 0.0f;               // CI:110-114
+    ps.a = a; ps.depth = 0;
+    ps.rng = path_rng(P.seed, ae * (uint64_t) P.spp_total + (uint64_t) s);      // RNG contract, SURVEY.md 8(d)
+}
+
+struct Counters {
+    unsigned paths, segments, rays, deposits, misses;
+};
+
+// executes ONE segment of the path; returns false when the path terminates.  rec != nullptr records decisions.
+__device__ __forceinline__ bool segment(const AcqDev &P, const DPrim *prims, PathState &ps, Counters &cn, prt_seg_record *rec) {
+    Hit h;
+    cn.rays++;
+    if (!closest_hit(P.sc, prims, ps.o, ps.d, PRT_INF, h)) { cn.misses++; return false; }   // CI:146-147 / 309-312
+    cn.segments++;
+    const float dist = h.t;
+    ps.geo += dist;                                                              // CI:209 / 315
+    const float tof_here = ps.tof + dist / P.c;                                  // CI:165 / 316
+    if (!(P.qf & PRT_QF_TOF_LAST_SEGMENT)) ps.tof = tof_here;
+    const float u_recv = ps.rng.next_f32();                                      // CI:153 / 319
+    const float s1 = ps.rng.next_f32();                                          // CI:173 / 337
+    const float s2 = ps.rng.next_f32();                                          // CI:174 / 337
+    const float u_rr = ps.rng.next_f32();                                        // CI:219 / 365
+    int recv = min((int) floorf(u_recv * (float) P.n_e), P.n_e - 1);             // CI:154
+    const float3 tgt = xpoint(P.T0, P.T1, P.T2, mk3(elem_x(P, recv), 0.0f, 0.0f));   // CI:156-157
+    const float3 to_t = tgt - h.p;
+    const float dist_recv = sqrtf(dot(to_t, to_t));                              // CI:166 / 329
+    const float3 sec = mk3(to_t.x / dist_recv, to_t.y / dist_recv, to_t.z / dist_recv);   // CI:158 / 322
+    const float3 so = spawn_origin(h.p, h.ng, sec);
+    float vis_tmax = PRT_INF;                                                    // Q1: maxt = inf
+    if (P.qf & PRT_QF_CONNECT_TO_TARGET) {
+        float3 q = tgt - so;
+        vis_tmax = sqrtf(dot(q, q)) * (1.0f - 1e-4f);
+    }
+    cn.rays++;
+    const bool visible = !occluded(P.sc, prims, so, sec, vis_tmax);              // CI:159-160 / 324-325
+    ps.atten *= expf((P.att_k * dist) / 8.686f);                                 // CI:162-163 / 328
+    const float Ttot = (ps.t0 + tof_here) + dist_recv / P.c;                     // CI:167 / 329
+    const float phase = P.two_pi_f * Ttot;                                       // CI:168 / 330
+    const float3 md = -ps.d;
+    const float3 wi = mk3(dot(md, h.fs), dot(md, h.ft), dot(md, h.ns));          // si.wi
+    const DMaterial &mat = P.sc.mats[h.material];
+    float3 dir; float pdf, a_resp; bool reflect;
+    ultra_bsdf_sample(wi, h.ng, h.ns, __ldg(&mat.p[0]), __ldg(&mat.p[1]), s1, s2, dir, pdf, a_resp, reflect);   // CI:175 / 338
+    const float cos_theta = dot(h.ns, md);                                       // CI:176 / 340
+    ps.amp *= a_resp * cos_theta * fmaxf(pdf, 1e-6f);                            // CI:177 / 341
+    const float al = fabsf(acosf(dot(P.nT, -sec)));                              // CI:124-126
+    const float w_i = al <= P.alpha_m ? 1.0f : (al <= P.alpha_c ? (P.alpha_c - al) / (P.alpha_c - P.alpha_m) : 0.0f);   // CI:128-133
+    const float w_o = dot(ps.d, h.ns) / P.n_rays;                                // CI:118,184
+    const float press = ps.atten * ps.amp * (w_i * w_o) * sinf(phase);           // CI:187 / 348
+    const float kf = rintf(Ttot * P.fs);                                         // CI:191 / 351-352 (half-even)
+    int k = (int) kf;
+    bool in_range = kf >= 0.0f && kf < (float) P.Tn;
+    if (P.qf & PRT_QF_CLAMP_TIDX) {                                              // CI:192
+        k = !(kf >= 0.0f) ? 0 : (kf > (float) (P.Tn - 1) ? P.Tn - 1 : k);
+        in_range = true;
+    }
+    if (visible && in_range) {
+        if (P.buf) atomicAdd(P.buf + ((size_t) ps.a * P.n_e + recv) * (size_t) P.Tn + (size_t) k, press * P.inv_spp);   // CI:197-203 / 354
+        cn.deposits++;
+    }
+    ps.d = normalize(dir);                                                       // CI:205-206 / 358-359 (Q9)
+    ps.o = spawn_origin(h.p, h.ng, ps.d);
+    ps.depth++;                                                                  // CI:210 / 361
+    const float prod = ps.atten * ps.amp;
+    const float rr = (P.qf & PRT_QF_RR_NO_ABS) ? fminf(prod, 1.0f) : fminf(fabsf(prod), 1.0f);   // CI:220 / 364
+    const bool survive = u_rr < rr;                                              // CI:221
+    ps.atten = survive ? ps.atten / rr : 0.0f;                                   // CI:224
+    if (rec) {
+        prt_seg_record &r = rec[ps.depth - 1];
+        r.valid = 1; r.prim = h.prim; r.shape = h.shape; r.recv = recv; r.visible = visible; r.reflect = reflect;
+        r.k = k; r.survive = survive; r.t = dist; r.total_time = Ttot; r.press = press; r.amp = ps.amp; r.atten = ps.atten;
+        r.dir[0] = ps.d.x; r.dir[1] = ps.d.y; r.dir[2] = ps.d.z;
+    }
+    if (P.qf & PRT_QF_SINGLE_BOUNCE) return false;
+    if (!survive || !(dot(ps.d, P.nT) >= P.cos_c)) return false;                 // CI:212-223 (Q11)
+    return ps.depth < P.max_depth && ps.geo < P.max_len;                         // CI:141 / 307
+}
+
+__device__ __forceinline__ const DPrim *stage_prims(const DScene &sc, DPrim *smem) {
+    if (sc.n_prims > MAX_SMEM_PRIMS) return sc.prims;
+    const float4 *src = reinterpret_cast<const float4 *>(sc.prims);
+    float4 *dst = reinterpret_cast<float4 *>(smem);
+    for (int i = threadIdx.x; i < sc.n_prims * (int) (sizeof(DPrim) / 16); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    return smem;
+}
+
+__global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const AcqDev P) {
+    __shared__ DPrim sprims[MAX_SMEM_PRIMS];
+    const DPrim *prims = stage_prims(P.sc, sprims);
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t n_ae = (uint64_t) P.n_a * (uint64_t) P.n_e;
+    // transmit-delay table, CI:87-94 / 254-257
+    if (P.tx && j < n_ae) {
+        float2 sc = __ldg(P.sincos + (int) (j / (uint64_t) P.n_e));
+        P.tx[j] = (elem_x(P, (int) (j % (uint64_t) P.n_e)) * sc.x) / P.c;
+    }
+    Counters cn = { 0, 0, 0, 0, 0 };
+    PathState ps;
+    bool live = false;
+    for (;;) {
+        if (!live) {
+            if (j >= P.total) break;
+            // sample-major launch order: consecutive lanes -> consecutive (angle, element), same sample
+            uint64_t ae = j % n_ae, si = j / n_ae;
+            init_path(P, ae, P.s_offset + (uint32_t) si * P.s_stride, ps);
+            j += stride;
+            cn.paths++;
+            live = P.max_depth > 0;
+            if (!live) continue;
+        }
+        live = segment(P, prims, ps, cn, nullptr);
+    }
+    if (P.stats) {
+        unsigned v[5] = { cn.paths, cn.segments, cn.rays, cn.deposits, cn.misses };
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            unsigned x = v[q];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) == 0 && x) atomicAdd(P.stats + q, (unsigned long long) x);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ACQ_THREADS) k_acquire_trace(const AcqDev P, const uint64_t *__restrict__ path_idx, uint64_t n,
+                                                                prt_seg_record *rec) {
+    __shared__ DPrim sprims[MAX_SMEM_PRIMS];
+    const DPrim *prims = stage_prims(P.sc, sprims);
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t path = path_idx[i];
+    PathState ps;
+    Counters cn = { 0, 0, 0, 0, 0 };
+    init_path(P, path / P.spp_total, (uint32_t) (path % P.spp_total), ps);
+    bool live = P.max_depth > 0;
+    while (live) live = segment(P, prims, ps, cn, rec + i * (uint64_t) P.max_depth);
+}
+
+static int fill_params(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t s_offset,
+                       uint32_t s_stride, AcqDev &P, cudaStream_t st) {
+    PRT_REQUIRE(p->n_angles > 0 && p->n_elements > 0 && p->time_samples > 0 && p->max_depth >= 0 && p->angles_deg,
+                "acquire: invalid acquisition parameters");
+    PRT_REQUIRE(spp_total > 0, "acquire: spp_total must be > 0");
+    PRT_REQUIRE((uint64_t) p->n_angles * p->n_elements * (uint64_t) p->time_samples < (1ull << 40), "acquire: channel buffer too large");
+    prt_context *c = s->ctx;
+    int rc = ensure_scratch(c, 0, 0, (size_t) p->n_angles);
+    if (rc) return rc;
+    // per-angle (sin, cos) in fp32 exactly as the reference forms them: theta = angle * pi / 180 (CI:78)
+    std::vector<float2> sc(p->n_angles);
+    for (int a = 0; a < p->n_angles; a++) {
+        float theta = (float) p->angles_deg[a] * (float) M_PI / 180.0f;
+        sc[a] = make_float2(sinf(theta), cosf(theta));
+    }
+    PRT_CUDA(cudaMemcpyAsync(c->angles_dev, sc.data(), sizeof(float2) * p->n_angles, cudaMemcpyHostToDevice, st));
+    PRT_CUDA(cudaStreamSynchronize(st));  // sc is a stack temporary
+    const double *m = p->sensor_to_world;
+    P.sc = s->view();
+    P.T0 = make_float4((float) m[0], (float) m[1], (float) m[2], (float) m[3]);
+    P.T1 = make_float4((float) m[4], (float) m[5], (float) m[6], (float) m[7]);
+    P.T2 = make_float4((float) m[8], (float) m[9], (float) m[10], (float) m[11]);
+    float nx = P.T0.z, ny = P.T1.z, nz = P.T2.z;  // T * (0,0,1)
+    float nl = sqrtf(nx * nx + ny * ny + nz * nz);
+    P.nT = make_float3(nx / nl, ny / nl, nz / nl);
+    P.c = (float) p->sound_speed;
+    P.fs = (float) p->fs;
+    P.pitch = (float) p->pitch;
+    P.two_pi_f = (float) (2.0 * M_PI * p->frequency);
+    P.att_k = (float) (-p->attenuation * p->frequency * 1e-6);
+    P.alpha_m = (float) (p->main_beam_deg * M_PI / 180.0);
+    P.alpha_c = (float) (p->cutoff_deg * M_PI / 180.0);
+    P.cos_c = cosf(P.alpha_c);
+    P.max_len = (float) p->max_path_len;
+    P.n_rays = (float) (p->n_angles * p->n_elements);
+    P.inv_spp = 1.0f / (float) spp_total;
+    P.n_a = p->n_angles;
+    P.n_e = p->n_elements;
+    P.Tn = p->time_samples;
+    P.max_depth = p->max_depth;
+    P.qf = p->quirk_flags;
+    P.sincos = reinterpret_cast<const float2 *>(c->angles_dev);
+    P.seed = seed;
+    P.spp_total = spp_total;
+    P.s_offset = s_offset;
+    P.s_stride = s_stride ? s_stride : 1;
+    P.n_s = s_offset < spp_total ? ((uint64_t) spp_total - s_offset + P.s_stride - 1) / P.s_stride : 0;
+    P.total = P.n_s * (uint64_t) p->n_angles * (uint64_t) p->n_elements;
+    P.buf = nullptr;
+    P.tx = nullptr;
+    P.stats = nullptr;
+    return PRT_OK;
+}
+
+static int launch_acquire(prt_context *c, const AcqDev &P, cudaStream_t st) {
+    // persistent grid: a whole number of CTAs per SM (occupancy-derived), never more than the work needs
+    int per_sm = 0;
+    PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acquire, ACQ_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    uint64_t want = (P.total + ACQ_THREADS - 1) / ACQ_THREADS;
+    uint64_t n_ae_blocks = ((uint64_t) P.n_a * P.n_e + ACQ_THREADS - 1) / ACQ_THREADS;
+    if (want < n_ae_blocks) want = n_ae_blocks;  // the tx-delay table is written by the first n_a*n_e threads
+    uint64_t grid = (uint64_t) c->sm_count * per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    k_acquire<<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_OK;
+}
+
+}  // namespace prt
+
+using namespace prt;
+
+extern "C" {
+
+int prt_acquire_dev(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                    uint32_t sample_stride, float *channel_buf_dev, float *tx_delays_dev, uint64_t *stats_dev, void *stream) {
+    PRT_REQUIRE(s && p && channel_buf_dev, "prt_acquire_dev: null argument");
+    if (!s->committed) { set_error("prt_acquire_dev: scene not committed"); return PRT_ERR_STATE; }
+    std::lock_guard<std::mutex> lk(s->ctx->mtx);
+    PRT_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    AcqDev P;
+    int rc = fill_params(s, p, seed, spp_total, sample_offset, sample_stride, P, st);
+    if (rc) return rc;
+    P.buf = channel_buf_dev;
+    P.tx = tx_delays_dev;
+    P.stats = reinterpret_cast<unsigned long long *>(stats_dev);
+    return launch_acquire(s->ctx, P, st);
+}
+
+int prt_acquire(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                uint32_t sample_stride, float *channel_buf, float *tx_delays, prt_acq_stats *stats) {
+    PRT_REQUIRE(s && p && channel_buf, "prt_acquire: null argument");
+    if (!s->committed) { set_error("prt_acquire: scene not committed"); return PRT_ERR_STATE; }
+    std::lock_guard<std::mutex> lk(s->ctx->mtx);
+    prt_context *c = s->ctx;
+    PRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    AcqDev P;
+    int rc = fill_params(s, p, seed, spp_total, sample_offset, sample_stride, P, st);
+    if (rc) return rc;
+    const size_t n_buf = (size_t) p->n_angles * p->n_elements * (size_t) p->time_samples;
+    const size_t n_tx = (size_t) p->n_angles * p->n_elements;
+    rc = ensure_scratch(c, n_buf, n_tx, (size_t) p->n_angles);
+    if (rc) return rc;
+    cudaEvent_t e0, e1, e2, e3;
+    PRT_CUDA(cudaEventCreate(&e0)); PRT_CUDA(cudaEventCreate(&e1)); PRT_CUDA(cudaEventCreate(&e2)); PRT_CUDA(cudaEventCreate(&e3));
+    PRT_CUDA(cudaEventRecord(e0, st));
+    PRT_CUDA(cudaMemsetAsync(c->acc_dev, 0, sizeof(float) * n_buf, st));
+    PRT_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(uint64_t) * 8, st));
+    P.buf = c->acc_dev;
+    P.tx = c->aux_dev;
+    P.stats = reinterpret_cast<unsigned long long *>(c->stats_dev);
+    PRT_CUDA(cudaEventRecord(e1, st));
+    rc = launch_acquire(c, P, st);
+    if (rc) return rc;
+    PRT_CUDA(cudaEventRecord(e2, st));
+    // D2H through the pinned staging buffer, then into the caller's (pageable) arrays
+    float *pin = reinterpret_cast<float *>(c->pinned);
+    PRT_CUDA(cudaMemcpyAsync(pin, c->acc_dev, sizeof(float) * n_buf, cudaMemcpyDeviceToHost, st));
+    PRT_CUDA(cudaMemcpyAsync(pin + n_buf, c->aux_dev, sizeof(float) * n_tx, cudaMemcpyDeviceToHost, st));
+    uint64_t hs[8];
+    PRT_CUDA(cudaMemcpyAsync(hs, c->stats_dev, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
+    PRT_CUDA(cudaEventRecord(e3, st));
+    PRT_CUDA(cudaStreamSynchronize(st));
+    memcpy(channel_buf, pin, sizeof(float) * n_buf);
+    if (tx_delays) memcpy(tx_delays, pin + n_buf, sizeof(float) * n_tx);
+    if (stats) {
+        stats->paths = hs[0]; stats->segments = hs[1]; stats->rays = hs[2]; stats->deposits = hs[3]; stats->misses = hs[4];
+        PRT_CUDA(cudaEventElapsedTime(&stats->kernel_ms, e1, e2));
+        PRT_CUDA(cudaEventElapsedTime(&stats->total_ms, e0, e3));
+        stats->launches = 1;
+        stats->_pad = 0;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    return PRT_OK;
+}
+
+int prt_acquire_trace(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, const uint64_t *path_idx,
+                      uint64_t n, prt_seg_record *rec) {
+    PRT_REQUIRE(s && p && path_idx && rec, "prt_acquire_trace: null argument");
+    if (!s->committed) { set_error("prt_acquire_trace: scene not committed"); return PRT_ERR_STATE; }
+    if (n == 0) return PRT_OK;
+    std::lock_guard<std::mutex> lk(s->ctx->mtx);
+    prt_context *c = s->ctx;
+    PRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    AcqDev P;
+    int rc = fill_params(s, p, seed, spp_total, 0, 1, P, st);
+    if (rc) return rc;
+    const uint64_t limit = (uint64_t) p->n_angles * p->n_elements * (uint64_t) spp_total;
+    for (uint64_t i = 0; i < n; i++) PRT_REQUIRE(path_idx[i] < limit, "prt_acquire_trace: path index out of range");
+    uint64_t *idx_d = nullptr;
+    prt_seg_record *rec_d = nullptr;
+    const size_t nrec = (size_t) n * (size_t) (p->max_depth > 0 ? p->max_depth : 1);
+    PRT_CUDA(cudaMalloc(&idx_d, sizeof(uint64_t) * n));
+    PRT_CUDA(cudaMalloc(&rec_d, sizeof(prt_seg_record) * nrec));
+    PRT_CUDA(cudaMemcpyAsync(idx_d, path_idx, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
+    PRT_CUDA(cudaMemsetAsync(rec_d, 0, sizeof(prt_seg_record) * nrec, st));
+    k_acquire_trace<<<(unsigned) ((n + ACQ_THREADS - 1) / ACQ_THREADS), ACQ_THREADS, 0, st>>>(P, idx_d, n, rec_d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rec, rec_d, sizeof(prt_seg_record) * (size_t) n * (size_t) p->max_depth, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(idx_d);
+    cudaFree(rec_d);
+    PRT_CUDA(e);
+    return PRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// prt_internal.h -- host-side state behind the C ABI (include/prt_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/prt_b200.h"
+#include "prt_device.cuh"
+
+namespace prt {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define PRT_CUDA(call)                                                       \
+    do {                                                                     \
+        cudaError_t _e = (call);                                             \
+        if (_e != cudaSuccess) return prt::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define PRT_REQUIRE(cond, msg)               \
+    do {                                     \
+        if (!(cond)) {                       \
+            prt::set_error(msg);             \
+            return PRT_ERR_INVALID;          \
+        }                                    \
+    } while (0)
+
+struct HostMesh {
+    std::vector<float> v;   // [nt][3][3] world space
+    std::vector<float> n;   // [nt][3][3] world-space corner normals (if has_n)
+    bool has_n;
+    int  shape, material, flip;
+    uint32_t nt;
+};
+
+}  // namespace prt
+
+struct prt_context {
+    int device;
+    int sm_count;
+    cudaDeviceProp prop;
+    std::mutex mtx;
+    cudaStream_t stream;          // library-owned stream for the host-buffer entry points
+    // scratch for the acquisition / render entry points (grown on demand, reused across calls)
+    float    *acc_dev;   size_t acc_cap;      // accumulator (channel_buf / film)
+    float    *aux_dev;   size_t aux_cap;      // tx_delays etc.
+    uint64_t *stats_dev;                      // 8 x u64
+    double   *angles_dev; size_t angles_cap;
+    void     *pinned;    size_t pinned_cap;   // pinned staging for D2H of results
+};
+
+struct prt_scene {
+    prt_context *ctx;
+    std::vector<prt::DPrim>     prims;
+    std::vector<prt::DMaterial> mats;
+    std::vector<prt::HostMesh>  meshes;
+    int  n_shapes;
+    bool committed;
+    // device
+    prt::DPrim     *prims_dev;
+    prt::DMaterial *mats_dev;
+    float4 *nodes_dev, *tri_v_dev, *tri_n_dev;
+    int4   *tri_info_dev;
+    uint32_t n_tris, n_nodes;
+    int root_ref;
+    uint64_t device_bytes;
+    prt_bvh_stats stats;
+    prt::DScene view() const;
+};
+
+namespace prt {
+// prt_bvh.cu: builds the LBVH over `n` triangles given in INPUT order.
+//   tri_v_in  [n][3] float4 world-space vertices (device), reordered into tri_v_out in sorted order
+//   order_out [n] sorted position -> input index
+int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri_v_out, uint32_t *order_out,
+               float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t stream);
+int ensure_scratch(prt_context *ctx, size_t acc_floats, size_t aux_floats, size_t n_angles);
+}  // namespace prt

@@ -1,0 +1,387 @@
+// prt_scene.cu -- context + scene container behind the C ABI: host-side assembly of analytic primitives,
+// materials and world-space triangle soup, upload to device-resident float4 SoA buffers, LBVH build.
+// Replaces mi.set_variant / mi.load_dict / mi.traverse(...).update() (/root/reference/USMain.py:12,257-265).
+#include <cmath>
+#include <cstring>
+
+#include "prt_internal.h"
+
+namespace prt {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in `" + what + "` at " + file + ":" + std::to_string(line);
+    return PRT_ERR_CUDA;
+}
+
+static bool invert_affine(const double m[16], double inv[12]) {
+    double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    if (det == 0.0 || !std::isfinite(det)) return false;
+    double id = 1.0 / det;
+    double r[9] = { (e * i - f * h) * id, (c * h - b * i) * id, (b * f - c * e) * id, (f * g - d * i) * id, (a * i - c * g) * id,
+                    (c * d - a * f) * id, (d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id };
+    for (int k = 0; k < 3; k++) {
+        inv[4 * k] = r[3 * k];
+        inv[4 * k + 1] = r[3 * k + 1];
+        inv[4 * k + 2] = r[3 * k + 2];
+        inv[4 * k + 3] = -(r[3 * k] * m[3] + r[3 * k + 1] * m[7] + r[3 * k + 2] * m[11]);
+    }
+    return true;
+}
+
+int ensure_scratch(prt_context *ctx, size_t acc_floats, size_t aux_floats, size_t n_angles) {
+    if (acc_floats > ctx->acc_cap) {
+        if (ctx->acc_dev) cudaFree(ctx->acc_dev);
+        ctx->acc_dev = nullptr;
+        ctx->acc_cap = 0;
+        PRT_CUDA(cudaMalloc(&ctx->acc_dev, sizeof(float) * acc_floats));
+        ctx->acc_cap = acc_floats;
+    }
+    if (aux_floats > ctx->aux_cap) {
+        if (ctx->aux_dev) cudaFree(ctx->aux_dev);
+        ctx->aux_dev = nullptr;
+        ctx->aux_cap = 0;
+        PRT_CUDA(cudaMalloc(&ctx->aux_dev, sizeof(float) * aux_floats));
+        ctx->aux_cap = aux_floats;
+    }
+    if (n_angles > ctx->angles_cap) {
+        if (ctx->angles_dev) cudaFree(ctx->angles_dev);
+        ctx->angles_dev = nullptr;
+        ctx->angles_cap = 0;
+        PRT_CUDA(cudaMalloc(&ctx->angles_dev, sizeof(double) * n_angles));
+        ctx->angles_cap = n_angles;
+    }
+    size_t need = sizeof(float) * (acc_floats + aux_floats);
+    if (need > ctx->pinned_cap) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_cap = 0;
+        PRT_CUDA(cudaMallocHost(&ctx->pinned, need));
+        ctx->pinned_cap = need;
+    }
+    return PRT_OK;
+}
+
+}  // namespace prt
+
+using namespace prt;
+
+prt::DScene prt_scene::view() const {
+    DScene v;
+    v.prims = prims_dev;
+    v.mats = mats_dev;
+    v.nodes = nodes_dev;
+    v.tri_v = tri_v_dev;
+    v.tri_n = tri_n_dev;
+    v.tri_info = tri_info_dev;
+    v.n_prims = (int) prims.size();
+    v.n_mats = (int) mats.size();
+    v.n_tris = (int) n_tris;
+    v.root_ref = root_ref;
+    return v;
+}
+
+extern "C" {
+
+const char *prt_last_error(void) { return g_last_error.c_str(); }
+const char *prt_version(void) { return "prt_b200 0.1.0 (sm_100a)"; }
+
+int prt_device_count(int *count) {
+    PRT_REQUIRE(count, "prt_device_count: null output");
+    *count = 0;
+    PRT_CUDA(cudaGetDeviceCount(count));
+    return PRT_OK;
+}
+
+int prt_create(int device, prt_context **out) {
+    PRT_REQUIRE(out, "prt_create: null output");
+    *out = nullptr;
+    int n = 0;
+    PRT_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) {
+        set_error("prt_create: no such CUDA device " + std::to_string(device) + " (" + std::to_string(n) + " visible); there is no CPU fallback");
+        return PRT_ERR_CUDA;
+    }
+    PRT_CUDA(cudaSetDevice(device));
+    prt_context *c = new prt_context();
+    c->device = device;
+    PRT_CUDA(cudaGetDeviceProperties(&c->prop, device));
+    c->sm_count = c->prop.multiProcessorCount;
+    c->acc_dev = c->aux_dev = nullptr;
+    c->acc_cap = c->aux_cap = 0;
+    c->angles_dev = nullptr;
+    c->angles_cap = 0;
+    c->pinned = nullptr;
+    c->pinned_cap = 0;
+    c->stats_dev = nullptr;
+    PRT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PRT_CUDA(cudaMalloc(&c->stats_dev, sizeof(uint64_t) * 8));
+    *out = c;
+    return PRT_OK;
+}
+
+int prt_destroy(prt_context *c) {
+    if (!c) return PRT_OK;
+    cudaSetDevice(c->device);
+    if (c->acc_dev) cudaFree(c->acc_dev);
+    if (c->aux_dev) cudaFree(c->aux_dev);
+    if (c->angles_dev) cudaFree(c->angles_dev);
+    if (c->stats_dev) cudaFree(c->stats_dev);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return PRT_OK;
+}
+
+int prt_device_info(prt_context *c, int *sm_count, int *cc_major, int *cc_minor, uint64_t *global_mem_bytes) {
+    PRT_REQUIRE(c, "prt_device_info: null context");
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->prop.major;
+    if (cc_minor) *cc_minor = c->prop.minor;
+    if (global_mem_bytes) *global_mem_bytes = (uint64_t) c->prop.totalGlobalMem;
+    return PRT_OK;
+}
+
+int prt_scene_create(prt_context *c, prt_scene **out) {
+    PRT_REQUIRE(c && out, "prt_scene_create: null argument");
+    prt_scene *s = new prt_scene();
+    s->ctx = c;
+    s->n_shapes = 0;
+    s->committed = false;
+    s->prims_dev = nullptr;
+    s->mats_dev = nullptr;
+    s->nodes_dev = s->tri_v_dev = s->tri_n_dev = nullptr;
+    s->tri_info_dev = nullptr;
+    s->n_tris = s->n_nodes = 0;
+    s->root_ref = -1;
+    s->device_bytes = 0;
+    memset(&s->stats, 0, sizeof s->stats);
+    *out = s;
+    return PRT_OK;
+}
+
+static void free_device(prt_scene *s) {
+    cudaSetDevice(s->ctx->device);
+    if (s->prims_dev) cudaFree(s->prims_dev);
+    if (s->mats_dev) cudaFree(s->mats_dev);
+    if (s->nodes_dev) cudaFree(s->nodes_dev);
+    if (s->tri_v_dev) cudaFree(s->tri_v_dev);
+    if (s->tri_n_dev) cudaFree(s->tri_n_dev);
+    if (s->tri_info_dev) cudaFree(s->tri_info_dev);
+    s->prims_dev = nullptr;
+    s->mats_dev = nullptr;
+    s->nodes_dev = s->tri_v_dev = s->tri_n_dev = nullptr;
+    s->tri_info_dev = nullptr;
+    s->device_bytes = 0;
+}
+
+int prt_scene_destroy(prt_scene *s) {
+    if (!s) return PRT_OK;
+    std::lock_guard<std::mutex> lk(s->ctx->mtx);
+    free_device(s);
+    delete s;
+    return PRT_OK;
+}
+
+int prt_scene_add_material(prt_scene *s, int kind, const double p[8], const double emission_rgb[3], int *material_id) {
+    PRT_REQUIRE(s, "prt_scene_add_material: null scene");
+    PRT_REQUIRE(kind >= PRT_MAT_ULTRA && kind <= PRT_MAT_NULL, "prt_scene_add_material: unknown material kind");
+    DMaterial m;
+    memset(&m, 0, sizeof m);
+    m.kind = kind;
+    for (int i = 0; i < 7; i++) m.p[i] = p ? (float) p[i] : 0.0f;
+    for (int i = 0; i < 3; i++) m.emission[i] = emission_rgb ? (float) emission_rgb[i] : 0.0f;
+    s->mats.push_back(m);
+    s->committed = false;
+    if (material_id) *material_id = (int) s->mats.size() - 1;
+    return PRT_OK;
+}
+
+int prt_scene_set_material_param(prt_scene *s, int material_id, int index, double value) {
+    PRT_REQUIRE(s, "prt_scene_set_material_param: null scene");
+    PRT_REQUIRE(material_id >= 0 && material_id < (int) s->mats.size() && index >= 0 && index < 7,
+                "prt_scene_set_material_param: index out of range");
+    std::lock_guard<std::mutex> lk(s->ctx->mtx);
+    s->mats[material_id].p[index] = (float) value;
+    if (s->committed && s->mats_dev) {
+        PRT_CUDA(cudaSetDevice(s->ctx->device));
+        PRT_CUDA(cudaMemcpy(s->mats_dev + material_id, &s->mats[material_id], sizeof(DMaterial), cudaMemcpyHostToDevice));
+    }
+    return PRT_OK;
+}
+
+int prt_scene_add_primitive(prt_scene *s, int kind, const double to_world[16], int material_id, int flip_normals, int *shape_id) {
+    PRT_REQUIRE(s && to_world, "prt_scene_add_primitive: null argument");
+    PRT_REQUIRE(kind >= PRT_SPHERE && kind <= PRT_CYLINDER, "prt_scene_add_primitive: unknown primitive kind");
+    PRT_REQUIRE(material_id >= 0 && material_id < (int) s->mats.size(), "prt_scene_add_primitive: unknown material");
+    double inv[12];
+    PRT_REQUIRE(invert_affine(to_world, inv), "prt_scene_add_primitive: singular to_world");
+    DPrim p;
+    const double *m = to_world;
+    p.w0 = make_float4((float) m[0], (float) m[1], (float) m[2], (float) m[3]);
+    p.w1 = make_float4((float) m[4], (float) m[5], (float) m[6], (float) m[7]);
+    p.w2 = make_float4((float) m[8], (float) m[9], (float) m[10], (float) m[11]);
+    p.o0 = make_float4((float) inv[0], (float) inv[1], (float) inv[2], (float) inv[3]);
+    p.o1 = make_float4((float) inv[4], (float) inv[5], (float) inv[6], (float) inv[7]);
+    p.o2 = make_float4((float) inv[8], (float) inv[9], (float) inv[10], (float) inv[11]);
+    if (kind == PRT_SPHERE) {
+        // centre = to_world*(0,0,0), radius = |to_world*(1,0,0)|
+        double r = std::sqrt(m[0] * m[0] + m[4] * m[4] + m[8] * m[8]);
+        p.aux = make_float4((float) m[3], (float) m[7], (float) m[11], (float) r);
+    } else {
+        // world normal of the object-space +z plane: normalize(inverse-transpose * (0,0,1)), fp32 like the oracle
+        float nx = (float) inv[8], ny = (float) inv[9], nz = (float) inv[10];
+        float l = std::sqrt(nx * nx + ny * ny + nz * nz);
+        p.aux = make_float4(nx / l, ny / l, nz / l, 0.0f);
+    }
+    p.kind = kind;
+    p.material = material_id;
+    p.flip = flip_normals ? 1 : 0;
+    p.shape = s->n_shapes;
+    s->prims.push_back(p);
+    s->committed = false;
+    if (shape_id) *shape_id = s->n_shapes;
+    s->n_shapes++;
+    return PRT_OK;
+}
+
+int prt_scene_add_mesh(prt_scene *s, const double *v, uint32_t nv, const double *vn, const uint32_t *idx, uint32_t nt,
+                       const double to_world[16], int material_id, int flip_normals, int *shape_id) {
+    PRT_REQUIRE(s && v && idx && to_world, "prt_scene_add_mesh: null argument");
+    PRT_REQUIRE(material_id >= 0 && material_id < (int) s->mats.size(), "prt_scene_add_mesh: unknown material");
+    double inv[12];
+    PRT_REQUIRE(invert_affine(to_world, inv), "prt_scene_add_mesh: singular to_world");
+    HostMesh hm;
+    hm.has_n = vn != nullptr;
+    hm.shape = s->n_shapes;
+    hm.material = material_id;
+    hm.flip = flip_normals ? 1 : 0;
+    hm.nt = nt;
+    hm.v.resize((size_t) nt * 9);
+    if (vn) hm.n.resize((size_t) nt * 9);
+    const double *m = to_world;
+    for (uint32_t t = 0; t < nt; t++) {
+        for (int c = 0; c < 3; c++) {
+            uint32_t vi = idx[3 * (size_t) t + c];
+            if (vi >= nv) {
+                set_error("prt_scene_add_mesh: vertex index out of range");
+                return PRT_ERR_INVALID;
+            }
+            const double *p = v + 3 * (size_t) vi;
+            for (int r = 0; r < 3; r++)
+                hm.v[9 * (size_t) t + 3 * c + r] = (float) (m[4 * r] * p[0] + m[4 * r + 1] * p[1] + m[4 * r + 2] * p[2] + m[4 * r + 3]);
+            if (vn) {
+                const double *n = vn + 3 * (size_t) vi;
+                double w[3];
+                for (int r = 0; r < 3; r++) w[r] = inv[r] * n[0] + inv[4 + r] * n[1] + inv[8 + r] * n[2];
+                double l = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+                for (int r = 0; r < 3; r++) hm.n[9 * (size_t) t + 3 * c + r] = l > 0 ? (float) (w[r] / l) : 0.0f;
+            }
+        }
+    }
+    s->meshes.push_back(std::move(hm));
+    s->committed = false;
+    if (shape_id) *shape_id = s->n_shapes;
+    s->n_shapes++;
+    return PRT_OK;
+}
+
+__global__ void k_gather_aux(const uint32_t *__restrict__ order, uint32_t n, const int4 *__restrict__ info_in,
+                             const float4 *__restrict__ n_in, int4 *info_out, float4 *n_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t src = order[i];
+    info_out[i] = info_in[src];
+    if (n_in) {
+        n_out[3 * (size_t) i] = n_in[3 * (size_t) src];
+        n_out[3 * (size_t) i + 1] = n_in[3 * (size_t) src + 1];
+        n_out[3 * (size_t) i + 2] = n_in[3 * (size_t) src + 2];
+    }
+}
+
+int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
+    PRT_REQUIRE(s, "prt_scene_commit: null scene");
+    std::lock_guard<std::mutex> lk(s->ctx->mtx);
+    PRT_CUDA(cudaSetDevice(s->ctx->device));
+    free_device(s);
+    memset(&s->stats, 0, sizeof s->stats);
+    cudaStream_t st = s->ctx->stream;
+    size_t bytes = 0;
+    if (!s->prims.empty()) {
+        PRT_CUDA(cudaMalloc(&s->prims_dev, sizeof(DPrim) * s->prims.size()));
+        PRT_CUDA(cudaMemcpy(s->prims_dev, s->prims.data(), sizeof(DPrim) * s->prims.size(), cudaMemcpyHostToDevice));
+        bytes += sizeof(DPrim) * s->prims.size();
+    }
+    if (!s->mats.empty()) {
+        PRT_CUDA(cudaMalloc(&s->mats_dev, sizeof(DMaterial) * s->mats.size()));
+        PRT_CUDA(cudaMemcpy(s->mats_dev, s->mats.data(), sizeof(DMaterial) * s->mats.size(), cudaMemcpyHostToDevice));
+        bytes += sizeof(DMaterial) * s->mats.size();
+    }
+    uint64_t nt = 0;
+    bool any_n = false;
+    for (auto &m : s->meshes) {
+        nt += m.nt;
+        any_n |= m.has_n;
+    }
+    PRT_REQUIRE(nt < (1ull << 29), "prt_scene_commit: too many triangles (limit 2^29)");
+    s->n_tris = (uint32_t) nt;
+    s->root_ref = -1;
+    if (nt) {
+        // host staging in input order: float4 vertices, int4 info, float4 normals
+        std::vector<float4> hv(nt * 3), hn(any_n ? nt * 3 : 0);
+        std::vector<int4> hi(nt);
+        size_t o = 0;
+        for (auto &m : s->meshes) {
+            for (uint32_t t = 0; t < m.nt; t++, o++) {
+                for (int c = 0; c < 3; c++) {
+                    hv[3 * o + c] = make_float4(m.v[9 * (size_t) t + 3 * c], m.v[9 * (size_t) t + 3 * c + 1], m.v[9 * (size_t) t + 3 * c + 2], 0.0f);
+                    if (any_n)
+                        hn[3 * o + c] = m.has_n ? make_float4(m.n[9 * (size_t) t + 3 * c], m.n[9 * (size_t) t + 3 * c + 1], m.n[9 * (size_t) t + 3 * c + 2], 0.0f)
+                                                : make_float4(0, 0, 0, 0);
+                }
+                hi[o] = make_int4((int) o, m.shape, m.material, (m.has_n ? 1 : 0) | (m.flip ? 2 : 0));
+            }
+        }
+        float4 *v_in = nullptr, *n_in = nullptr;
+        int4 *i_in = nullptr;
+        uint32_t *order = nullptr;
+        PRT_CUDA(cudaMalloc(&v_in, sizeof(float4) * 3 * nt));
+        PRT_CUDA(cudaMalloc(&i_in, sizeof(int4) * nt));
+        PRT_CUDA(cudaMalloc(&order, sizeof(uint32_t) * nt));
+        PRT_CUDA(cudaMemcpy(v_in, hv.data(), sizeof(float4) * 3 * nt, cudaMemcpyHostToDevice));
+        PRT_CUDA(cudaMemcpy(i_in, hi.data(), sizeof(int4) * nt, cudaMemcpyHostToDevice));
+        if (any_n) {
+            PRT_CUDA(cudaMalloc(&n_in, sizeof(float4) * 3 * nt));
+            PRT_CUDA(cudaMemcpy(n_in, hn.data(), sizeof(float4) * 3 * nt, cudaMemcpyHostToDevice));
+            PRT_CUDA(cudaMalloc(&s->tri_n_dev, sizeof(float4) * 3 * nt));
+            bytes += sizeof(float4) * 3 * nt;
+        }
+        PRT_CUDA(cudaMalloc(&s->tri_v_dev, sizeof(float4) * 3 * nt));
+        PRT_CUDA(cudaMalloc(&s->tri_info_dev, sizeof(int4) * nt));
+        PRT_CUDA(cudaMalloc(&s->nodes_dev, sizeof(float4) * 4 * (nt > 1 ? nt - 1 : 1)));
+        bytes += sizeof(float4) * 3 * nt + sizeof(int4) * nt + sizeof(float4) * 4 * (nt > 1 ? nt - 1 : 1);
+        int rc = build_lbvh(s->ctx, v_in, (uint32_t) nt, s->tri_v_dev, order, s->nodes_dev, &s->root_ref, &s->stats, st);
+        if (rc) return rc;
+        k_gather_aux<<<(unsigned) ((nt + 255) / 256), 256, 0, st>>>(order, (uint32_t) nt, i_in, n_in, s->tri_info_dev, s->tri_n_dev);
+        PRT_CUDA(cudaStreamSynchronize(st));
+        PRT_CUDA(cudaGetLastError());
+        cudaFree(v_in);
+        cudaFree(i_in);
+        cudaFree(order);
+        if (n_in) cudaFree(n_in);
+        s->n_nodes = s->stats.n_nodes;
+    }
+    s->device_bytes = bytes;
+    s->stats.n_primitives = (uint32_t) s->prims.size();
+    s->stats.n_triangles = s->n_tris;
+    s->stats.device_bytes = bytes;
+    s->committed = true;
+    if (out) *out = s->stats;
+    return PRT_OK;
+}
+
+}  // extern "C"

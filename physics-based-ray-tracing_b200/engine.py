@@ -1,0 +1,186 @@
+"""Device engine: owns a ``prt_context`` + ``prt_scene`` and exposes the hot path to the plugin layer.
+
+``DeviceScene`` is what ``mi.load_dict`` / ``mi.load_file`` hand back underneath the Mitsuba-style
+``Scene`` object: the scene uploaded once to device-resident SoA buffers with the LBVH built on the GPU,
+then ``trace_closest`` (== ``scene.ray_intersect``, /root/reference/CustomIntegrator.py:146,309),
+``acquire`` (== ``UltraIntegrator.simulate_acquisition*``, :60-405) and ``render_path``.
+All compute goes through the C ABI (capi.py); nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import capi
+from .capi import PrtError, check, dptr, fptr
+from .scene import AcqParams, SceneDesc
+
+_contexts: Dict[int, "Context"] = {}
+_ctx_lock = threading.Lock()
+
+
+class Context:
+    """One per (process, device)."""
+
+    def __init__(self, device: int = 0):
+        self.L = capi.load()
+        self.device = device
+        h = C.c_void_p()
+        check(self.L.prt_create(device, C.byref(h)), "prt_create")
+        self.h = h
+        sm, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
+        check(self.L.prt_device_info(h, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem)))
+        self.sm_count, self.cc, self.global_mem = sm.value, (maj.value, mnr.value), mem.value
+
+    @staticmethod
+    def get(device: Optional[int] = None) -> "Context":
+        if device is None:
+            import os
+            device = int(os.environ.get("LOCAL_RANK", "0")) if "PRT_DEVICE" not in os.environ else int(os.environ["PRT_DEVICE"])
+            n = C.c_int()
+            L = capi.load()
+            check(L.prt_device_count(C.byref(n)), "prt_device_count")
+            if n.value == 0:
+                raise PrtError("no CUDA device visible; the acquisition / render path has no CPU fallback")
+            device %= n.value
+        with _ctx_lock:
+            c = _contexts.get(device)
+            if c is None:
+                c = Context(device)
+                _contexts[device] = c
+            return c
+
+
+class DeviceScene:
+    def __init__(self, desc: SceneDesc, device: Optional[int] = None, context: Optional[Context] = None):
+        self.ctx = context or Context.get(device)
+        self.L = self.ctx.L
+        self.desc = desc
+        h = C.c_void_p()
+        check(self.L.prt_scene_create(self.ctx.h, C.byref(h)), "prt_scene_create")
+        self.h = h
+        out = C.c_int()
+        for m in desc.materials:
+            p = np.zeros(8)
+            p[:len(m.params)] = m.params
+            e = np.ascontiguousarray(m.emission, dtype=np.float64)
+            check(self.L.prt_scene_add_material(h, capi.MAT_KINDS[m.kind], dptr(p), dptr(e), C.byref(out)))
+        for s in desc.shapes:
+            tw = np.ascontiguousarray(s.to_world, dtype=np.float64).reshape(16)
+            if s.kind == "mesh":
+                v = np.ascontiguousarray(s.v, dtype=np.float64).reshape(-1, 3)
+                vn = None if s.vn is None else np.ascontiguousarray(s.vn, dtype=np.float64).reshape(-1, 3)
+                idx = np.ascontiguousarray(s.idx, dtype=np.uint32).reshape(-1, 3)
+                check(self.L.prt_scene_add_mesh(h, dptr(v), v.shape[0], dptr(vn), idx.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                idx.shape[0], dptr(tw), s.material, int(s.flip_normals), C.byref(out)),
+                      "prt_scene_add_mesh")
+            else:
+                check(self.L.prt_scene_add_primitive(h, capi.PRIM_KINDS[s.kind], dptr(tw), s.material, int(s.flip_normals),
+                                                     C.byref(out)), "prt_scene_add_primitive")
+        st = capi.BvhStatsC()
+        check(self.L.prt_scene_commit(h, C.byref(st)), "prt_scene_commit")
+        self.bvh_stats = st.as_dict()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.prt_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- mi.traverse(scene)[...] = v; params.update() ------------------------------------------
+    def set_material_param(self, material: int, index: int, value: float):
+        check(self.L.prt_scene_set_material_param(self.h, material, index, float(value)), "prt_scene_set_material_param")
+
+    # -- scene.ray_intersect ----------------------------------------------------------------------
+    def trace_closest(self, o, d, tmax=None):
+        o = np.ascontiguousarray(o, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, dtype=np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        tm = None if tmax is None else np.ascontiguousarray(np.broadcast_to(tmax, (n,)), dtype=np.float32)
+        t = np.empty(n, dtype=np.float32)
+        prim = np.empty(n, dtype=np.int32)
+        shape = np.empty(n, dtype=np.int32)
+        p, ng, ns, wi, sh_s = (np.zeros((n, 3), dtype=np.float32) for _ in range(5))
+        ip = C.POINTER(C.c_int32)
+        check(self.L.prt_trace_closest(self.h, fptr(o), fptr(d), fptr(tm), n, fptr(t), prim.ctypes.data_as(ip),
+                                       shape.ctypes.data_as(ip), fptr(p), fptr(ng), fptr(ns), fptr(wi), fptr(sh_s)),
+              "prt_trace_closest")
+        return dict(t=t, prim=prim, shape=shape, p=p, ng=ng, ns=ns, wi=wi, sh_s=sh_s)
+
+    def trace_occluded(self, o, d, tmax=None):
+        o = np.ascontiguousarray(o, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, dtype=np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        tm = None if tmax is None else np.ascontiguousarray(np.broadcast_to(tmax, (n,)), dtype=np.float32)
+        hit = np.empty(n, dtype=np.uint8)
+        check(self.L.prt_trace_occluded(self.h, fptr(o), fptr(d), fptr(tm), n, hit.ctypes.data_as(C.POINTER(C.c_uint8))),
+              "prt_trace_occluded")
+        return hit.astype(bool)
+
+    # -- simulate_acquisition* ---------------------------------------------------------------------
+    def acquire(self, params: AcqParams, seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1):
+        """Host-buffer entry point: returns (channel_buf [n_a,n_e,T] f32, tx_delays [n_a,n_e] f32, stats)."""
+        ps = capi.make_acq_params(params)
+        buf = np.empty((params.n_angles, params.n_elements, params.time_samples), dtype=np.float32)
+        tx = np.empty((params.n_angles, params.n_elements), dtype=np.float32)
+        st = capi.AcqStatsC()
+        check(self.L.prt_acquire(self.h, C.byref(ps), seed, spp, sample_offset, sample_stride, fptr(buf), fptr(tx),
+                                 C.byref(st)), "prt_acquire")
+        return buf, tx, st.as_dict()
+
+    def acquire_dev(self, params: AcqParams, buf_ptr: int, tx_ptr: int = 0, stats_ptr: int = 0, stream: int = 0,
+                    seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1):
+        """Device-buffer entry point (accumulates into ``buf_ptr`` on ``stream``, asynchronous)."""
+        ps = capi.make_acq_params(params)
+        check(self.L.prt_acquire_dev(self.h, C.byref(ps), seed, spp, sample_offset, sample_stride, C.c_void_p(buf_ptr),
+                                     C.c_void_p(tx_ptr or None), C.c_void_p(stats_ptr or None), C.c_void_p(stream or None)),
+              "prt_acquire_dev")
+
+    def acquire_trace(self, params: AcqParams, path_idx, seed: int = 0, spp: int = 1) -> np.ndarray:
+        ps = capi.make_acq_params(params)
+        idx = np.ascontiguousarray(path_idx, dtype=np.uint64).reshape(-1)
+        rec = np.zeros((idx.size, max(params.max_depth, 1)), dtype=capi.SEG_DTYPE)
+        check(self.L.prt_acquire_trace(self.h, C.byref(ps), seed, spp, idx.ctypes.data_as(C.POINTER(C.c_uint64)), idx.size,
+                                       rec.ctypes.data_as(C.c_void_p)), "prt_acquire_trace")
+        return rec
+
+    # -- mi.render with the `path` integrator ------------------------------------------------------
+    def render_path(self, rp: "capi.RenderParamsC", seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1):
+        film = np.empty((rp.height, rp.width, 4), dtype=np.float32)
+        st = capi.RenderStatsC()
+        check(self.L.prt_render_path(self.h, C.byref(rp), seed, spp, sample_offset, sample_stride, fptr(film), C.byref(st)),
+              "prt_render_path")
+        return film, st.as_dict()
+
+    def render_path_dev(self, rp: "capi.RenderParamsC", film_ptr: int, stats_ptr: int = 0, stream: int = 0, seed: int = 0,
+                        spp: int = 1, sample_offset: int = 0, sample_stride: int = 1):
+        check(self.L.prt_render_path_dev(self.h, C.byref(rp), seed, spp, sample_offset, sample_stride, C.c_void_p(film_ptr),
+                                         C.c_void_p(stats_ptr or None), C.c_void_p(stream or None)), "prt_render_path_dev")
+
+
+def ultra_bsdf_sample(wi, ng, ns, impedance, roughness, s1, s2, context: Optional[Context] = None):
+    """Batched UltraBSDF.sample on the GPU (/root/reference/CustomBSDF.py:87-175)."""
+    ctx = context or Context.get()
+    wi = np.ascontiguousarray(wi, dtype=np.float32).reshape(-1, 3)
+    n = wi.shape[0]
+    ng = np.ascontiguousarray(np.broadcast_to(ng, (n, 3)), dtype=np.float32)
+    ns = np.ascontiguousarray(np.broadcast_to(ns, (n, 3)), dtype=np.float32)
+    z = np.ascontiguousarray(np.broadcast_to(impedance, (n,)), dtype=np.float32)
+    r = np.ascontiguousarray(np.broadcast_to(roughness, (n,)), dtype=np.float32)
+    a = np.ascontiguousarray(np.broadcast_to(s1, (n,)), dtype=np.float32)
+    b = np.ascontiguousarray(np.broadcast_to(s2, (n,)), dtype=np.float32)
+    d = np.empty((n, 3), dtype=np.float32)
+    pdf = np.empty(n, dtype=np.float32)
+    amp = np.empty(n, dtype=np.float32)
+    rf = np.empty(n, dtype=np.int32)
+    check(ctx.L.prt_ultra_bsdf_sample(ctx.h, n, fptr(wi), fptr(ng), fptr(ns), fptr(z), fptr(r), fptr(a), fptr(b), fptr(d),
+                                      fptr(pdf), fptr(amp), rf.ctypes.data_as(C.POINTER(C.c_int32))), "prt_ultra_bsdf_sample")
+    return d, pdf, amp, rf.astype(bool)

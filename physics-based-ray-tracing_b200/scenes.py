@@ -1,0 +1,253 @@
+"""Programmatic equivalents of the reference's scene files, for hosts where /root/reference is absent
+(the GPU box) and for the BASELINE.json configs that have no scene file at all.
+
+Each builder states the file it mirrors; tests/test_scene_loading.py checks (where /root/reference
+exists) that loading the original XML gives the same SceneDesc.  Numbers are the reference's:
+  * MitsubaScenes/*.xml  -- integrator / sensor block Sphere_Box.xml:2-34, shapes :36-101
+  * USMain.py:26-90      -- the driver's dict scene
+  * TestRing/TestRing.obj-- annulus r 0.05..0.06, z 0..0.05, 144 segments, 4 x 288 triangles, v//vn corners
+  * scenes/cbox.xml      -- Cornell box, quads of scenes/meshes/cbox_*.obj
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+
+from .meshio import heightfield_mesh
+from .scene import SceneDesc, load_dict_desc
+from .transforms import Transform4f, apply_xml_ops
+
+T = Transform4f
+
+
+def _xf(ops, order):
+    return apply_xml_ops(ops, order)
+
+
+def ultrasound_integrator_dict():
+    # MitsubaScenes/Sphere_Box.xml:2-15
+    return {"type": "ultrasound_integrator", "max_depth": 10, "sampling_rate": 50000000.0, "frequency": 3000000.0,
+            "sound_speed": 1480.0, "attenuation": 0.1, "wave_cycles": 5, "main_beam_angle": 24.0, "cutoff_angle": 30.0,
+            "n_elements": 64, "pitch": 0.00012, "time_samples": 10000,
+            "angles": np.array([-15.0, -7.5, 0.0, 7.5, 15.0])}
+
+
+def ultrasound_sensor_dict():
+    # MitsubaScenes/Sphere_Box.xml:16-34
+    return {"type": "ultrasound_sensor", "num_elements_lateral": 1280, "elements_width": 0.003, "elements_height": 0.01,
+            "pitch": 0.0003, "radius": float("inf"), "center_frequency": 3000000.0, "sound_speed": 1480.0,
+            "directivity": 1.0, "to_world": T().look_at([0, 0, 0.0], [0, 0, 0.05], [0, 1, 0]),
+            "film": {"type": "hdrfilm", "width": 512, "height": 512, "pixel_format": "luminance",
+                     "component_format": "float32"}}
+
+
+def _ubsdf(rough):
+    return {"type": "ultrasound_bsdf", "impedance": 7.8, "roughness": rough}
+
+
+def _box_walls(order):
+    # MitsubaScenes/Sphere_Box.xml:47-101
+    R, S, Tr = (lambda ax, a: T().rotate(ax, a)), (lambda v: T().scale(v)), (lambda v: T().translate(v))
+    walls = {
+        "box_back": [Tr([0, 0, 0.37]), R([0, 1, 0], 180), S([0.15, 0.15, 1])],
+        "box_left": [Tr([-0.15, 0, 0.12]), R([0, 1, 0], 90), S([0.25, 0.15, 1])],
+        "box_right": [Tr([0.15, 0, 0.12]), R([0, 1, 0], -90), S([0.25, 0.15, 1])],
+        "box_top": [Tr([0, 0.15, 0.12]), R([1, 0, 0], 90), S([0.15, 0.25, 1])],
+        "box_bottom": [Tr([0, -0.15, 0.12]), R([1, 0, 0], -90), S([0.15, 0.25, 1])],
+    }
+    return {k: {"type": "rectangle", "to_world": _xf(ops, order), "bsdf": _ubsdf(0.7)} for k, ops in walls.items()}
+
+
+MITSUBA_SCENES = {
+    # file stem -> (target, boxed)
+    "Sphere_Box": ("sphere", True), "Sphere_Floating": ("sphere", False),
+    "Cone_Box": ("cone", True), "Cone_FLoating": ("cone", False),
+    "Plate_Box": ("plate", True), "Plane_Floating": ("plate", False),
+}
+
+
+def ultrasound_scene_dict(name: str, order: str = "mitsuba") -> dict:
+    """The six analytic-primitive scenes of /root/reference/MitsubaScenes/ as load_dict input."""
+    target, boxed = MITSUBA_SCENES[name]
+    d = {"type": "scene", "integrator": ultrasound_integrator_dict(), "sensor": ultrasound_sensor_dict()}
+    if target == "sphere":      # Sphere_Box.xml:36-45
+        d["sphere"] = {"type": "sphere", "to_world": _xf([T().translate([0, 0, 0.08]), T().scale(0.06)], order),
+                       "bsdf": _ubsdf(0.9)}
+    elif target == "cone":      # Cone_Box.xml:36-47
+        d["cone"] = {"type": "cone", "to_world": _xf([T().translate([0, 0, 0.06]), T().rotate([1, 0, 0], -20),
+                                                      T().rotate([0, 1, 0], 25), T().scale([0.06, 0.06, 0.10])], order),
+                     "bsdf": _ubsdf(0.9)}
+    else:                       # Plate_Box.xml:36-46
+        d["plate"] = {"type": "rectangle", "to_world": _xf([T().translate([0, 0, 0.05]), T().rotate([0, 1, 0], 45),
+                                                            T().scale([0.17, 0.17, 0.02])], order), "bsdf": _ubsdf(0.9)}
+    if boxed:
+        d.update(_box_walls(order))
+    return d
+
+
+def ultrasound_scene(name: str, order: str = "mitsuba", registry=None) -> SceneDesc:
+    desc = load_dict_desc(ultrasound_scene_dict(name, order), registry)
+    desc.source = f"<builtin:{name}:{order}>"
+    return desc
+
+
+def usmain_scene_dict() -> dict:
+    """/root/reference/USMain.py:26-90."""
+    integ = {"type": "ultrasound_integrator", "max_depth": 10, "sampling_rate": 50e6, "frequency": 5e6, "sound_speed": 1540,
+             "attenuation": 0.2, "wave_cycles": 5, "main_beam_angle": 24, "cutoff_angle": 30, "n_elements": 64,
+             "pitch": 0.00003 * 4, "time_samples": 10000, "angles": np.linspace(-15.0, 15.0, 5)}
+    sensor = ultrasound_sensor_dict()
+    sensor.update({"center_frequency": 5e6, "sound_speed": 1540, "to_world": T().look_at([0, 0, 0.0], [0, 0, 0.03], [0, 1, 0])})
+    return {
+        "type": "scene", "integrator": integ, "sensor": sensor,
+        "flat_plate": {"type": "rectangle",
+                       "to_world": T().translate([0, 0, 0.05]) @ T().rotate([0, 1, 0], 45) @ T().scale([.17, .17, 0.14]),
+                       "bsdf": _ubsdf(0.7)},
+        "wall_back": {"type": "rectangle",
+                      "to_world": T().translate([0, 0, 1]) @ T().rotate([0, 1, 0], 180) @ T().scale([0.05, 0.05, 1]),
+                      "bsdf": _ubsdf(0.7)},
+    }
+
+
+def ring_mesh(r_in: float = 0.05, r_out: float = 0.06, height: float = 0.05, segments: int = 144):
+    """Procedural twin of TestRing/TestRing.obj: 4 groups (inner wall, outer wall, two caps) of
+    2*segments triangles, per-corner normals (smooth on the walls, flat on the caps)."""
+    ang = np.arange(segments + 1) * (2.0 * math.pi / segments)
+    c, s = np.cos(ang), np.sin(ang)
+    v, n, f = [], [], []
+
+    def quad(p, q):
+        base = len(v)
+        v.extend(p)
+        n.extend(q)
+        f.append((base, base + 1, base + 2))
+        f.append((base, base + 2, base + 3))
+
+    for i in range(segments):
+        j = i + 1
+        # inner wall: normal points to the axis
+        quad([(r_in * c[i], r_in * s[i], 0), (r_in * c[i], r_in * s[i], height), (r_in * c[j], r_in * s[j], height),
+              (r_in * c[j], r_in * s[j], 0)],
+             [(-c[i], -s[i], 0), (-c[i], -s[i], 0), (-c[j], -s[j], 0), (-c[j], -s[j], 0)])
+    for i in range(segments):
+        j = i + 1
+        quad([(r_out * c[i], r_out * s[i], 0), (r_out * c[j], r_out * s[j], 0), (r_out * c[j], r_out * s[j], height),
+              (r_out * c[i], r_out * s[i], height)],
+             [(c[i], s[i], 0), (c[j], s[j], 0), (c[j], s[j], 0), (c[i], s[i], 0)])
+    for z, nz in ((0.0, -1.0), (height, 1.0)):
+        for i in range(segments):
+            j = i + 1
+            p = [(r_in * c[i], r_in * s[i], z), (r_out * c[i], r_out * s[i], z), (r_out * c[j], r_out * s[j], z),
+                 (r_in * c[j], r_in * s[j], z)]
+            if nz < 0:
+                p = p[::-1]
+            quad(p, [(0, 0, nz)] * 4)
+    return np.array(v, dtype=np.float64), np.array(n, dtype=np.float64), np.array(f, dtype=np.uint32)
+
+
+def test_ring_scene_dict(mesh=None) -> dict:
+    """BASELINE.json config 3: the ring wrapped in the Sphere_Floating integrator /
+    sensor block (builder-supplied wrapper; the reference has no scene for this mesh).  The ring lies ACROSS
+    the beam -- axis along y, centred at (0, 0, 0.08) -- so that in the imaging plane y = 0 it presents the
+    same r = 0.06 outer surface as the *intended* Sphere_* scenes, backed by its 1 cm wall and the inner bore.
+    (Placing it coaxially with the array, as SURVEY.md first suggested, makes every primary ray pass through
+    the bore: x = z tan 15 deg <= 0.021 < r_in.)  Z 7.8 / roughness 0.9."""
+    v, vn, idx = mesh if mesh is not None else ring_mesh()
+    to_world = T().translate([0, 0.025, 0.08]) @ T().rotate([1, 0, 0], 90)
+    return {"type": "scene", "integrator": ultrasound_integrator_dict(), "sensor": ultrasound_sensor_dict(),
+            "ring": {"type": "mesh", "vertices": v, "normals": vn, "faces": idx, "to_world": to_world,
+                     "bsdf": _ubsdf(0.9)}}
+
+
+def test_ring_scene(mesh=None, registry=None) -> SceneDesc:
+    desc = load_dict_desc(test_ring_scene_dict(mesh), registry)
+    desc.source = "<builtin:TestRing>"
+    return desc
+
+
+def _quad(pts):
+    return {"type": "mesh", "vertices": np.array(pts, dtype=np.float64), "normals": None,
+            "faces": np.array([[0, 1, 2], [0, 2, 3]], dtype=np.uint32)}
+
+
+def cbox_scene_dict(res: int = 256, spp: int = 128, max_depth: int = 6) -> dict:
+    """/root/reference/scenes/cbox.xml (quads: scenes/meshes/cbox_*.obj).  The `ultraray` emitter block
+    (:64-84) becomes an area emitter with radiance = its `intensity` (1,1,1) -- SURVEY.md 8(d) C4."""
+    d = {
+        "type": "scene",
+        "integrator": {"type": "path", "max_depth": max_depth},
+        "sensor": {"type": "perspective", "fov_axis": "smaller", "near_clip": 0.001, "far_clip": 100.0,
+                   "focus_distance": 1000.0, "fov": 39.3077, "to_world": T().look_at([0, 0, 4], [0, 0, 0], [0, 1, 0]),
+                   "sampler": {"type": "independent", "sample_count": spp},
+                   "film": {"type": "hdrfilm", "width": res, "height": res, "pixel_format": "rgb",
+                            "component_format": "float32", "rfilter": {"type": "tent"}}},
+        "gray": {"type": "diffuse", "reflectance": [0.85, 0.85, 0.85]},
+        "white": {"type": "diffuse", "reflectance": [0.885809, 0.698859, 0.666422]},
+        "green": {"type": "diffuse", "reflectance": [0.105421, 0.37798, 0.076425]},
+        "red": {"type": "diffuse", "reflectance": [0.570068, 0.0430135, 0.0443706]},
+        "glass": {"type": "dielectric"},
+        "mirror": {"type": "conductor"},
+    }
+    ref = lambda k: {"type": "ref", "id": k}
+    light = _quad([(0.25, 1, -0.25), (0.25, 1, 0.25), (-0.25, 1, 0.25), (-0.25, 1, -0.25)])
+    light.update({"to_world": T().translate([0, -0.01, 0]), "bsdf": ref("white"),
+                  "emitter": {"type": "ultraray", "intensity": [1.0, 1.0, 1.0]}})
+    d["light"] = light
+    quads = {
+        "floor": ([(-1, -1, 1), (1, -1, 1), (1, -1, -1), (-1, -1, -1)], "white"),
+        "ceiling": ([(1, 1, -1), (1, 1, 1), (-1, 1, 1), (-1, 1, -1)], "white"),
+        "back": ([(1, -1, -1), (1, 1, -1), (-1, 1, -1), (-1, -1, -1)], "white"),
+        "greenwall": ([(-1, 1, -1), (-1, 1, 1), (-1, -1, 1), (-1, -1, -1)], "green"),
+        "redwall": ([(1, -1, 1), (1, 1, 1), (1, 1, -1), (1, -1, -1)], "red"),
+    }
+    for k, (pts, mat) in quads.items():
+        q = _quad(pts)
+        q["bsdf"] = ref(mat)
+        d[k] = q
+    d["mirrorsphere"] = {"type": "sphere", "to_world": _xf([T().scale(0.5), T().translate([-0.3, -0.5, 0.2])], "mitsuba"),
+                         "bsdf": ref("mirror")}
+    d["glasssphere"] = {"type": "sphere", "to_world": _xf([T().scale(0.25), T().translate([0.5, -0.75, -0.2])], "mitsuba"),
+                        "bsdf": ref("glass")}
+    return d
+
+
+def cbox_scene(res: int = 256, spp: int = 128, max_depth: int = 6) -> SceneDesc:
+    desc = load_dict_desc(cbox_scene_dict(res, spp, max_depth))
+    desc.source = "<builtin:cbox>"
+    return desc
+
+
+def heightfield_scene_dict(n: int = 2237, res=(3840, 2160), spp: int = 64) -> dict:
+    """BASELINE.json config 5: closed box, ceiling light quad, height-field floor of
+    2 (n-1)^2 triangles, all diffuse 0.5, exactly 8 bounces (max_depth 9, rr disabled by the caller)."""
+    v, _, idx = heightfield_mesh(n)
+    # height field z -> world y (floor), lifted to y = -1
+    floor = {"type": "mesh", "vertices": np.stack([v[:, 0], v[:, 2] - 1.0, -v[:, 1]], axis=1), "normals": None,
+             "faces": idx, "bsdf": {"type": "ref", "id": "grey"}}
+    d = {
+        "type": "scene", "integrator": {"type": "path", "max_depth": 9, "rr_depth": 1000},
+        "sensor": {"type": "perspective", "fov_axis": "smaller", "near_clip": 0.001, "far_clip": 100.0, "fov": 39.3077,
+                   "to_world": T().look_at([0, 0.2, 3.8], [0, -0.4, 0], [0, 1, 0]),
+                   "sampler": {"type": "independent", "sample_count": spp},
+                   "film": {"type": "hdrfilm", "width": res[0], "height": res[1], "rfilter": {"type": "tent"}}},
+        "grey": {"type": "diffuse", "reflectance": [0.5, 0.5, 0.5]},
+        "floor": floor,
+    }
+    ref = {"type": "ref", "id": "grey"}
+    walls = {
+        "ceiling": [(1, 1, -1), (1, 1, 1), (-1, 1, 1), (-1, 1, -1)],
+        "back": [(1, -1.2, -1), (1, 1, -1), (-1, 1, -1), (-1, -1.2, -1)],
+        "left": [(-1, 1, -1), (-1, 1, 1), (-1, -1.2, 1), (-1, -1.2, -1)],
+        "right": [(1, -1.2, 1), (1, 1, 1), (1, 1, -1), (1, -1.2, -1)],
+        "front": [(-1, -1.2, 1), (-1, 1, 1), (1, 1, 1), (1, -1.2, 1)],
+    }
+    for k, pts in walls.items():
+        q = _quad(pts)
+        q["bsdf"] = ref
+        d[k] = q
+    light = _quad([(0.5, 0.99, -0.5), (0.5, 0.99, 0.5), (-0.5, 0.99, 0.5), (-0.5, 0.99, -0.5)])
+    light.update({"bsdf": ref, "emitter": {"type": "area", "radiance": [10.0, 10.0, 10.0]}})
+    d["light"] = light
+    return d
