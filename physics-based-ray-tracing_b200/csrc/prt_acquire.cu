@@ -59,10 +59,11 @@ struct Counters {
 };
 
 // executes ONE segment of the path; returns false when the path terminates.  rec != nullptr records decisions.
+template <bool TRIS>
 __device__ __forceinline__ bool segment(const AcqDev &P, const DPrim *prims, PathState &ps, Counters &cn, prt_seg_record *rec) {
     Hit h;
     cn.rays++;
-    if (!closest_hit(P.sc, prims, ps.o, ps.d, PRT_INF, h)) { cn.misses++; return false; }   // CI:146-147 / 309-312
+    if (!closest_hit<TRIS>(P.sc, prims, ps.o, ps.d, PRT_INF, h)) { cn.misses++; return false; }   // CI:146-147 / 309-312
     cn.segments++;
     const float dist = h.t;
     ps.geo += dist;                                                              // CI:209 / 315
@@ -84,7 +85,7 @@ __device__ __forceinline__ bool segment(const AcqDev &P, const DPrim *prims, Pat
         vis_tmax = sqrtf(dot(q, q)) * (1.0f - 1e-4f);
     }
     cn.rays++;
-    const bool visible = !occluded(P.sc, prims, so, sec, vis_tmax);              // CI:159-160 / 324-325
+    const bool visible = !occluded<TRIS>(P.sc, prims, so, sec, vis_tmax);              // CI:159-160 / 324-325
     ps.atten *= expf((P.att_k * dist) / 8.686f);                                 // CI:162-163 / 328
     const float Ttot = (ps.t0 + tof_here) + dist_recv / P.c;                     // CI:167 / 329
     const float phase = P.two_pi_f * Ttot;                                       // CI:168 / 330
@@ -137,7 +138,10 @@ __device__ __forceinline__ const DPrim *stage_prims(const DScene &sc, DPrim *sme
     return smem;
 }
 
-__global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const AcqDev P) {
+// occupancy targets: the analytic-only specialisation has no traversal stack and fits 4 CTAs/SM (64 regs);
+// the BVH one is held at 3 CTAs/SM (80 regs)
+template <bool TRIS>
+__global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const AcqDev P) {
     __shared__ DPrim sprims[MAX_SMEM_PRIMS];
     const DPrim *prims = stage_prims(P.sc, sprims);
     const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const AcqDev P) {
             live = P.max_depth > 0;
             if (!live) continue;
         }
-        live = segment(P, prims, ps, cn, nullptr);
+        live = segment<TRIS>(P, prims, ps, cn, nullptr);
     }
     if (P.stats) {
         unsigned v[5] = { cn.paths, cn.segments, cn.rays, cn.deposits, cn.misses };
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire_trace(const AcqDev P, c
     Counters cn = { 0, 0, 0, 0, 0 };
     init_path(P, path / P.spp_total, (uint32_t) (path % P.spp_total), ps);
     bool live = P.max_depth > 0;
-    while (live) live = segment(P, prims, ps, cn, rec + i * (uint64_t) P.max_depth);
+    while (live) live = segment<true>(P, prims, ps, cn, rec + i * (uint64_t) P.max_depth);
 }
 
 static int fill_params(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t s_offset,
@@ -246,8 +250,10 @@ static int fill_params(prt_scene *s, const prt_acq_params *p, uint64_t seed, uin
 
 static int launch_acquire(prt_context *c, const AcqDev &P, cudaStream_t st) {
     // persistent grid: a whole number of CTAs per SM (occupancy-derived), never more than the work needs
+    const bool tris = P.sc.n_tris > 0;
     int per_sm = 0;
-    PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acquire, ACQ_THREADS, 0));
+    if (tris) PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acquire<true>, ACQ_THREADS, 0));
+    else PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acquire<false>, ACQ_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     uint64_t want = (P.total + ACQ_THREADS - 1) / ACQ_THREADS;
     uint64_t n_ae_blocks = ((uint64_t) P.n_a * P.n_e + ACQ_THREADS - 1) / ACQ_THREADS;
@@ -255,7 +261,8 @@ static int launch_acquire(prt_context *c, const AcqDev &P, cudaStream_t st) {
     uint64_t grid = (uint64_t) c->sm_count * per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    k_acquire<<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
+    if (tris) k_acquire<true><<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
+    else k_acquire<false><<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
     PRT_CUDA(cudaGetLastError());
     return PRT_OK;
 }

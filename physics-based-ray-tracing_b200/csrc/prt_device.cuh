@@ -352,8 +352,20 @@ __device__ __forceinline__ int traverse_bvh(const DScene &sc, float3 o, float3 d
     float stack_t[PRT_STACK];
     int sp = 0, best = -1;
     int ref = sc.root_ref;
+    const int DONE = 0x7fffffff;
+    // pop the next entry whose box still starts before the current best hit
+#define PRT_POP()                                                        \
+    do {                                                                 \
+        ref = DONE;                                                      \
+        while (sp > 0) {                                                 \
+            --sp;                                                        \
+            if (stack_t[sp] <= tbest) { ref = stack_ref[sp]; break; }    \
+        }                                                                \
+    } while (0)
+    // "while-while" traversal (Aila & Laine 2009): all lanes first descend inner nodes until each holds a
+    // leaf (or is done), then the warp tests triangles together -- node and leaf code never interleave
     for (;;) {
-        if (ref >= 0) {
+        while ((unsigned) ref < (unsigned) DONE) {
             const float4 *n = sc.nodes + 4 * (size_t) ref;
             float4 q0 = ldg4(n), q1 = ldg4(n + 1), q2 = ldg4(n + 2), q3 = ldg4(n + 3);
             float tl = box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tbest);
@@ -368,11 +380,14 @@ __device__ __forceinline__ int traverse_bvh(const DScene &sc, float3 o, float3 d
                     sp++;
                 }
                 ref = lf ? rl : rr;
-                continue;
+            } else if (hl || hr) {
+                ref = hl ? rl : rr;
+            } else {
+                PRT_POP();
             }
-            if (hl) { ref = rl; continue; }
-            if (hr) { ref = rr; continue; }
-        } else {
+        }
+        if (ref == DONE) return best;
+        {
             int code = ~ref;
             int first = code >> 2, count = (code & 3) + 1;
             for (int j = 0; j < count; j++) {
@@ -384,13 +399,9 @@ __device__ __forceinline__ int traverse_bvh(const DScene &sc, float3 o, float3 d
                 }
             }
         }
-        // pop, culling entries that start beyond the current best
-        for (;;) {
-            if (sp == 0) return best;
-            --sp;
-            if (stack_t[sp] <= tbest) { ref = stack_ref[sp]; break; }
-        }
+        PRT_POP();
     }
+#undef PRT_POP
 }
 
 __device__ __forceinline__ void fill_tri_hit(const DScene &sc, int sorted_tri, float t, float b1, float b2, Hit &h) {
@@ -422,6 +433,8 @@ __device__ __forceinline__ void fill_tri_hit(const DScene &sc, int sorted_tri, f
 
 // scene.ray_intersect: nearest hit over analytic primitives (staged in shared memory by the caller)
 // and the triangle BVH
+// TRIS = false compiles the BVH traversal (and its stack) out: kernels specialised for analytic-only scenes
+template <bool TRIS = true>
 __device__ __forceinline__ bool closest_hit(const DScene &sc, const DPrim *prims, float3 o, float3 d, float tmax, Hit &h) {
     int best = -1;
     float tb = tmax;
@@ -432,21 +445,25 @@ __device__ __forceinline__ bool closest_hit(const DScene &sc, const DPrim *prims
             tb = t;
         }
     }
-    float b1 = 0.0f, b2 = 0.0f;
-    float tt = tb;
-    int tri = traverse_bvh<false>(sc, o, d, tt, b1, b2);
-    if (tri >= 0 && (best < 0 || tt < tb)) {
-        fill_tri_hit(sc, tri, tt, b1, b2, h);
-        return true;
+    if (TRIS) {
+        float b1 = 0.0f, b2 = 0.0f;
+        float tt = tb;
+        int tri = traverse_bvh<false>(sc, o, d, tt, b1, b2);
+        if (tri >= 0 && (best < 0 || tt < tb)) {
+            fill_tri_hit(sc, tri, tt, b1, b2, h);
+            return true;
+        }
     }
     if (best < 0) return false;
     fill_prim_hit(prims[best], best, o, d, tb, h);
     return true;
 }
 
+template <bool TRIS = true>
 __device__ __forceinline__ bool occluded(const DScene &sc, const DPrim *prims, float3 o, float3 d, float tmax) {
-    for (int i = 0; i < sc.n_prims; i++)
-        if (intersect_prim(prims[i], o, d, tmax) >= 0.0f) return true;
+    bool hit = false;
+    for (int i = 0; i < sc.n_prims; i++) hit |= intersect_prim(prims[i], o, d, tmax) >= 0.0f;
+    if (hit || !TRIS) return hit;
     float b1, b2, tt = tmax;
     return traverse_bvh<true>(sc, o, d, tt, b1, b2) >= 0;
 }

@@ -104,14 +104,15 @@ ratio = Z1 / Z2
 Ar0 = (Z1 - Z2) / (Z1 + Z2)
 out["ultra_bsdf"] = {"snells_ratio": ratio, "tir_angle_deg": math.degrees(math.asin(1 / ratio)), "Ar_normal": Ar0,
                      "At_normal": 1 - Ar0, "p_reflect_normal": Ar0 * Ar0}
-# a fully worked sample at normal incidence on a +z surface, s1 = 0.5 (disk centre -> m = -wi side), s2 given
-out["ultra_bsdf"]["normal_incidence"] = {"wi": [0.0, 0.0, 1.0], "n": [0.0, 0.0, 1.0], "s1": 0.5,
-                                         "refl_dir": [0.0, 0.0, -1.0], "pdf_reflect": 0.25,
-                                         "trans_dir": [0.0, 0.0, -(ratio) + (ratio - 1.0) * -1.0 * -1.0 - 2 * 0],
-                                         }
-# (trans = ratio*refl + (ratio*cTr - cTt)*m with m = (0,0,-1), cTr = 1, cTt = 1 -> (0,0,-ratio) + (ratio-1)(0,0,-1))
-out["ultra_bsdf"]["normal_incidence"]["trans_dir"] = [0.0, 0.0, -ratio - (ratio - 1.0)]
-out["ultra_bsdf"]["normal_incidence"]["pdf_trans"] = ratio ** 2 * abs((-ratio - (ratio - 1.0)) * -1.0) / (1.0 * abs(-ratio - (ratio - 1.0)))
+# a fully worked sample at normal incidence on a +z surface, s1 = 0.5 (disk centre): the sampled micro-normal is
+# +z, flipped to m = -z by CB:100, so cwm = wi.m = -1, cTr = cTt = 1 and, LITERALLY as CB:130-131 write it,
+#   refl  = wi + 2 cwm m              = (0,0,1) + 2(-1)(0,0,-1) = (0,0,3)      (Q8: not a mirror direction)
+#   trans = ratio refl + (ratio cTr - cTt) m = 6.5 (0,0,3) + 5.5 (0,0,-1) = (0,0,14)
+refl = [0.0, 0.0, 3.0]
+trans = [0.0, 0.0, ratio * 3.0 - (ratio - 1.0)]
+out["ultra_bsdf"]["normal_incidence"] = {"wi": [0.0, 0.0, 1.0], "n": [0.0, 0.0, 1.0], "s1": 0.5, "refl_dir": refl,
+                                         "pdf_reflect": 0.25, "trans_dir": trans,
+                                         "pdf_trans": ratio ** 2 * abs(trans[2] * -1.0) / (1.0 * abs(trans[2]))}
 
 # attenuation per metre -- CustomIntegrator.py:162
 out["atten_per_metre"] = {"xml": math.exp(-0.1 * 3e6 * 1e-6 / 8.686), "usmain": math.exp(-0.2 * 5e6 * 1e-6 / 8.686)}
