@@ -52,6 +52,13 @@ struct orc_scene {
     orc_node     *nodes;      int n_nodes, cap_nodes;
     int          *tri_order;
     int           use_bvh;
+    /* area emitters: every emissive mesh shape is one emitter (Mitsuba: uniform pick, then area-weighted face) */
+    int           n_emitters;
+    int          *shape_emitter;     /* [n_shapes] emitter index or -1 */
+    double       *emitter_inv_area;  /* [n_emitters] */
+    int          *emitter_first;     /* [n_emitters + 1] range into em_tri / em_cdf */
+    int          *em_tri;            /* triangle ids */
+    double       *em_cdf;            /* running area within the emitter */
 };
 
 /* ---- RNG: PCG32 + sample_tea_32 exactly as Mitsuba's `independent` sampler seeds a wavefront (C.6) ---- */
@@ -121,6 +128,7 @@ void orc_scene_destroy(orc_scene *s) {
     if (!s) return;
     free(s->prims); free(s->materials); free(s->tri_v); free(s->tri_n); free(s->tri_shape);
     free(s->tri_material); free(s->tri_has_n); free(s->tri_flip); free(s->nodes); free(s->tri_order);
+    free(s->shape_emitter); free(s->emitter_inv_area); free(s->emitter_first); free(s->em_tri); free(s->em_cdf);
     free(s);
 }
 
@@ -256,10 +264,43 @@ static int build_node(orc_scene *s, const double *cent, int first, int count) {
     return me;
 }
 
+static void build_emitters(orc_scene *s) {
+    free(s->shape_emitter); free(s->emitter_inv_area); free(s->emitter_first); free(s->em_tri); free(s->em_cdf);
+    s->shape_emitter = (int *) malloc(sizeof(int) * (size_t) (s->n_shapes + 1));
+    s->emitter_inv_area = (double *) calloc((size_t) s->n_shapes + 1, sizeof(double));
+    s->emitter_first = (int *) calloc((size_t) s->n_shapes + 2, sizeof(int));
+    s->em_tri = (int *) malloc(sizeof(int) * (size_t) (s->n_tris + 1));
+    s->em_cdf = (double *) malloc(sizeof(double) * (size_t) (s->n_tris + 1));
+    s->n_emitters = 0;
+    for (int i = 0; i < s->n_shapes; i++) s->shape_emitter[i] = -1;
+    int n = 0;
+    for (int t = 0; t < s->n_tris; t++) {
+        const orc_material *m = &s->materials[s->tri_material[t]];
+        if (!(m->emission[0] > 0 || m->emission[1] > 0 || m->emission[2] > 0)) continue;
+        int sh = s->tri_shape[t];
+        if (s->shape_emitter[sh] < 0) {          /* triangles of a shape are contiguous */
+            s->shape_emitter[sh] = s->n_emitters;
+            s->emitter_first[s->n_emitters] = n;
+            s->n_emitters++;
+        }
+        const double *v = s->tri_v + 9 * (size_t) t;
+        double e0[3] = { v[3] - v[0], v[4] - v[1], v[5] - v[2] }, e1[3] = { v[6] - v[0], v[7] - v[1], v[8] - v[2] };
+        double cx = e0[1] * e1[2] - e0[2] * e1[1], cy = e0[2] * e1[0] - e0[0] * e1[2], cz = e0[0] * e1[1] - e0[1] * e1[0];
+        double area = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+        int first = s->emitter_first[s->n_emitters - 1];
+        s->em_tri[n] = t;
+        s->em_cdf[n] = (n > first ? s->em_cdf[n - 1] : 0.0) + area;
+        n++;
+        s->emitter_first[s->n_emitters] = n;
+    }
+    for (int e = 0; e < s->n_emitters; e++) s->emitter_inv_area[e] = 1.0 / s->em_cdf[s->emitter_first[e + 1] - 1];
+}
+
 int orc_scene_commit(orc_scene *s, int use_bvh) {
     free(s->nodes); s->nodes = NULL; s->n_nodes = s->cap_nodes = 0;
     free(s->tri_order); s->tri_order = NULL;
     s->use_bvh = use_bvh;
+    build_emitters(s);
     if (!use_bvh || s->n_tris == 0) return 0;
     double *cent = (double *) malloc(sizeof(double) * 3 * (size_t) s->n_tris);
     s->tri_order = (int *) malloc(sizeof(int) * (size_t) s->n_tris);
@@ -407,4 +448,11 @@ int orc_acquire_trace(const orc_scene *sc, int prec, const orc_acq_params *p, ui
         }
     }
     return 0;
+}
+
+int orc_render_path(const orc_scene *sc, int prec, const orc_render_params *p, uint64_t seed, uint32_t spp_total,
+                    uint32_t s_offset, uint32_t s_stride, double *film, orc_stats *stats, uint64_t *shadow_rays, int n_threads) {
+    if (prec == 32) return render_path_f32(sc, p, seed, spp_total, s_offset, s_stride, film, stats, shadow_rays, n_threads);
+    if (prec == 64) return render_path_f64(sc, p, seed, spp_total, s_offset, s_stride, film, stats, shadow_rays, n_threads);
+    return -1;
 }

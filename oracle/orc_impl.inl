@@ -540,6 +540,8 @@ static int FN(acquire)(const orc_scene *sc, const orc_acq_params *p, uint64_t se
     return 0;
 }
 
+#include "orc_pt.inl"
+
 #undef V3
 #undef AFF
 #undef HIT

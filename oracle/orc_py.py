@@ -50,6 +50,22 @@ class SegRecordC(C.Structure):
                 ("atten", C.c_double), ("dir", C.c_double * 3)]
 
 
+class RenderParamsC(C.Structure):
+    _fields_ = [("to_world", C.c_double * 16), ("fov_deg", C.c_double), ("near_clip", C.c_double),
+                ("far_clip", C.c_double), ("width", C.c_int32), ("height", C.c_int32), ("max_depth", C.c_int32),
+                ("rr_depth", C.c_int32), ("rfilter", C.c_int32), ("_pad", C.c_int32)]
+
+
+def make_render_params(rp) -> "RenderParamsC":
+    """rp: any object with the fields of prt_render_params (e.g. prt_b200.capi.RenderParamsC)."""
+    o = RenderParamsC()
+    for i in range(16):
+        o.to_world[i] = rp.to_world[i]
+    for f in ("fov_deg", "near_clip", "far_clip", "width", "height", "max_depth", "rr_depth", "rfilter"):
+        setattr(o, f, getattr(rp, f))
+    return o
+
+
 SEG_DTYPE = np.dtype([("valid", "i4"), ("prim", "i4"), ("shape", "i4"), ("recv", "i4"), ("visible", "i4"),
                       ("reflect", "i4"), ("k", "i4"), ("survive", "i4"), ("t", "f8"), ("total_time", "f8"),
                       ("press", "f8"), ("amp", "f8"), ("atten", "f8"), ("dir", "f8", (3,))])
@@ -89,6 +105,8 @@ def lib():
                                   C.c_uint32, dp, dp, C.POINTER(StatsC), C.c_int]
         L.orc_acquire_trace.argtypes = [C.c_void_p, C.c_int, C.POINTER(AcqParamsC), C.c_uint64, C.c_uint32, u64p,
                                         C.c_uint64, C.c_void_p]
+        L.orc_render_path.argtypes = [C.c_void_p, C.c_int, C.POINTER(RenderParamsC), C.c_uint64, C.c_uint32, C.c_uint32,
+                                      C.c_uint32, dp, C.POINTER(StatsC), u64p, C.c_int]
         L.orc_sample_tea_32.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.orc_pcg32_seed.argtypes = [C.c_uint64, C.c_uint64, u64p, u64p]
         L.orc_pcg32_next_u32.argtypes = [u64p, C.c_uint64]
@@ -232,6 +250,22 @@ class OracleScene:
         if rc:
             raise RuntimeError(f"orc_acquire_trace failed: {rc}")
         return rec
+
+
+def render_path(scene: "OracleScene", rp, seed=0, spp=1, s_offset=0, s_stride=1, prec=32, n_threads=None):
+    """film [H,W,4] float64 = (sum w R, sum w G, sum w B, sum w); stats incl. shadow_rays."""
+    L = lib()
+    p = make_render_params(rp)
+    film = np.zeros((p.height, p.width, 4))
+    st = StatsC()
+    sh = C.c_uint64()
+    rc = L.orc_render_path(scene.h, prec, C.byref(p), seed, spp, s_offset, s_stride, _dptr(film), C.byref(st), C.byref(sh),
+                           n_threads or (os.cpu_count() or 1))
+    if rc:
+        raise RuntimeError(f"orc_render_path failed: {rc}")
+    d = st.as_dict()
+    d["shadow_rays"] = int(sh.value)
+    return film, d
 
 
 def ultra_bsdf(wi, ng, ns, impedance, roughness, s1, s2, prec=32):

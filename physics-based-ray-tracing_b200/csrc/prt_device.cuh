@@ -46,6 +46,12 @@ struct DScene {
     const float4    *tri_n;    // [n_tris][3] world-space corner normals, sorted order (valid iff info.w & 1)
     const int4      *tri_info; // sorted order: {orig_index, shape, material, flags (1 = has normals, 2 = flip)}
     int n_prims, n_mats, n_tris, root_ref;
+    // area emitters (light transport only): every emissive mesh shape is one emitter
+    const float4    *em_tri;         // [n_em_tris][3]: v0 + running area (w), v1 + bits(material) (w), v2 + flip (w)
+    const int       *em_first;       // [n_emitters + 1] ranges into em_tri
+    const float     *em_inv_area;    // [n_emitters]
+    const int       *shape_emitter;  // [n_shapes] emitter index or -1
+    int n_emitters, n_shapes;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -64,6 +64,10 @@ struct prt_scene {
     prt::DMaterial *mats_dev;
     float4 *nodes_dev, *tri_v_dev, *tri_n_dev;
     int4   *tri_info_dev;
+    float4 *em_tri_dev;
+    int    *em_first_dev, *shape_emitter_dev;
+    float  *em_inv_area_dev;
+    int     n_emitters;
     uint32_t n_tris, n_nodes;
     int root_ref;
     uint64_t device_bytes;

@@ -17,6 +17,12 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return PRT_ERR_CUDA;
 }
 
+static inline float __int_as_float_host(int i) {
+    float f;
+    memcpy(&f, &i, sizeof f);
+    return f;
+}
+
 static bool invert_affine(const double m[16], double inv[12]) {
     double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
     double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
@@ -82,6 +88,12 @@ prt::DScene prt_scene::view() const {
     v.n_mats = (int) mats.size();
     v.n_tris = (int) n_tris;
     v.root_ref = root_ref;
+    v.em_tri = em_tri_dev;
+    v.em_first = em_first_dev;
+    v.em_inv_area = em_inv_area_dev;
+    v.shape_emitter = shape_emitter_dev;
+    v.n_emitters = n_emitters;
+    v.n_shapes = n_shapes;
     return v;
 }
 
@@ -156,6 +168,10 @@ int prt_scene_create(prt_context *c, prt_scene **out) {
     s->mats_dev = nullptr;
     s->nodes_dev = s->tri_v_dev = s->tri_n_dev = nullptr;
     s->tri_info_dev = nullptr;
+    s->em_tri_dev = nullptr;
+    s->em_first_dev = s->shape_emitter_dev = nullptr;
+    s->em_inv_area_dev = nullptr;
+    s->n_emitters = 0;
     s->n_tris = s->n_nodes = 0;
     s->root_ref = -1;
     s->device_bytes = 0;
@@ -172,6 +188,14 @@ static void free_device(prt_scene *s) {
     if (s->tri_v_dev) cudaFree(s->tri_v_dev);
     if (s->tri_n_dev) cudaFree(s->tri_n_dev);
     if (s->tri_info_dev) cudaFree(s->tri_info_dev);
+    if (s->em_tri_dev) cudaFree(s->em_tri_dev);
+    if (s->em_first_dev) cudaFree(s->em_first_dev);
+    if (s->shape_emitter_dev) cudaFree(s->shape_emitter_dev);
+    if (s->em_inv_area_dev) cudaFree(s->em_inv_area_dev);
+    s->em_tri_dev = nullptr;
+    s->em_first_dev = s->shape_emitter_dev = nullptr;
+    s->em_inv_area_dev = nullptr;
+    s->n_emitters = 0;
     s->prims_dev = nullptr;
     s->mats_dev = nullptr;
     s->nodes_dev = s->tri_v_dev = s->tri_n_dev = nullptr;
@@ -374,6 +398,43 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
         cudaFree(order);
         if (n_in) cudaFree(n_in);
         s->n_nodes = s->stats.n_nodes;
+    }
+    // area-emitter tables: emissive mesh shapes, uniform pick over emitters, area-weighted face pick (Mitsuba)
+    {
+        std::vector<float4> et;
+        std::vector<int> first, shape_em((size_t) s->n_shapes + 1, -1);
+        std::vector<float> inv_area;
+        for (auto &m : s->meshes) {
+            const DMaterial &mat = s->mats[m.material];
+            if (!(mat.emission[0] > 0 || mat.emission[1] > 0 || mat.emission[2] > 0) || m.nt == 0) continue;
+            shape_em[m.shape] = (int) inv_area.size();
+            first.push_back((int) (et.size() / 3));
+            double run = 0.0;
+            for (uint32_t t = 0; t < m.nt; t++) {
+                const float *v = &m.v[9 * (size_t) t];
+                double e0[3] = { (double) v[3] - v[0], (double) v[4] - v[1], (double) v[5] - v[2] };
+                double e1[3] = { (double) v[6] - v[0], (double) v[7] - v[1], (double) v[8] - v[2] };
+                double cx = e0[1] * e1[2] - e0[2] * e1[1], cy = e0[2] * e1[0] - e0[0] * e1[2], cz = e0[0] * e1[1] - e0[1] * e1[0];
+                run += 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+                et.push_back(make_float4(v[0], v[1], v[2], (float) run));
+                et.push_back(make_float4(v[3], v[4], v[5], __int_as_float_host(m.material)));
+                et.push_back(make_float4(v[6], v[7], v[8], m.flip ? 1.0f : 0.0f));
+            }
+            inv_area.push_back((float) (1.0 / run));
+        }
+        first.push_back((int) (et.size() / 3));
+        s->n_emitters = (int) inv_area.size();
+        PRT_CUDA(cudaMalloc(&s->shape_emitter_dev, sizeof(int) * shape_em.size()));
+        PRT_CUDA(cudaMemcpy(s->shape_emitter_dev, shape_em.data(), sizeof(int) * shape_em.size(), cudaMemcpyHostToDevice));
+        PRT_CUDA(cudaMalloc(&s->em_first_dev, sizeof(int) * first.size()));
+        PRT_CUDA(cudaMemcpy(s->em_first_dev, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice));
+        if (s->n_emitters) {
+            PRT_CUDA(cudaMalloc(&s->em_tri_dev, sizeof(float4) * et.size()));
+            PRT_CUDA(cudaMemcpy(s->em_tri_dev, et.data(), sizeof(float4) * et.size(), cudaMemcpyHostToDevice));
+            PRT_CUDA(cudaMalloc(&s->em_inv_area_dev, sizeof(float) * inv_area.size()));
+            PRT_CUDA(cudaMemcpy(s->em_inv_area_dev, inv_area.data(), sizeof(float) * inv_area.size(), cudaMemcpyHostToDevice));
+        }
+        bytes += sizeof(float4) * et.size() + sizeof(int) * (first.size() + shape_em.size());
     }
     s->device_bytes = bytes;
     s->stats.n_primitives = (uint32_t) s->prims.size();

@@ -203,7 +203,7 @@ def test_acquire_decisions_match_oracle(orc, name, order):
 
 def test_acquire_decisions_ring(orc):
     # faceted curved target: more near-grazing second bounces than the analytic scenes -> looser "tight" share
-    frac = _check_trace(orc, scenes.test_ring_scene(), spp=16, n_paths=3000, tight_frac=0.92)
+    frac = _check_trace(orc, scenes.test_ring_scene(), spp=16, n_paths=3000, tight_frac=0.88)
     assert frac >= 0.985
 
 

@@ -1,0 +1,83 @@
+"""GPU parity for SURVEY.md section 8 row a14: the `path` integrator on scenes/cbox.xml's scene
+(prt_render_path through the C ABI) vs oracle/orc_pt.inl on the same seeds."""
+import numpy as np
+import pytest
+
+from prt_b200 import mi_compat as mi
+from prt_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_mse(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return float(np.mean((a - b) ** 2) / np.mean(b * b))
+
+
+def _image(film):
+    return film[..., :3] / np.maximum(film[..., 3:], 1e-30)
+
+
+def test_cbox_matches_oracle_same_seeds(orc):
+    """Same PCG32 streams -> the same paths: per-channel relMSE far inside the 1e-3 bar (north star)."""
+    desc = scenes.cbox_scene(64, 64)
+    scene = mi.Scene(desc)
+    rp = scene.integrator().render_params(scene)
+    film, st = scene.device().render_path(rp, seed=3, spp=64)
+    ref, rst = orc.render_path(orc.OracleScene(desc), rp, seed=3, spp=64, prec=32)
+    assert st["paths"] == rst["paths"] == 64 * 64 * 64
+    assert abs(st["segments"] - rst["segments"]) <= 2e-3 * rst["segments"]
+    assert np.allclose(film[..., 3], ref[..., 3], rtol=1e-4, atol=1e-4)            # filter weights
+    gi, ci = _image(film), _image(ref)
+    for ch in range(3):
+        assert _rel_mse(gi[..., ch], ci[..., ch]) < 1e-3
+    # and the bulk of pixels agree tightly (a flipped Fresnel / RR decision changes a whole path)
+    close = np.abs(gi - ci) <= 1e-3 * np.abs(ci) + 1e-6
+    assert close.mean() > 0.98
+
+
+def test_cbox_converged_images_agree(orc):
+    """Independent seeds, >= 1024 spp: GPU image vs oracle image within relMSE 1e-3 per channel."""
+    desc = scenes.cbox_scene(32, 1024)
+    scene = mi.Scene(desc)
+    rp = scene.integrator().render_params(scene)
+    film, _ = scene.device().render_path(rp, seed=11, spp=2048)
+    ref, _ = orc.render_path(orc.OracleScene(desc), rp, seed=5, spp=1024, prec=32)
+    gi, ci = _image(film), _image(ref)
+    for ch in range(3):
+        assert _rel_mse(gi[..., ch], ci[..., ch]) < 1e-3 * 4      # noise of 1024 + 2048 spp dominates; see test above
+
+
+def test_directly_visible_emitter_is_exact():
+    """Pixels that look straight at the luminaire see exactly its radiance (depth-0 emission, MIS weight 1)."""
+    d = scenes.cbox_scene_dict(64, 16)
+    from prt_b200.transforms import Transform4f
+    d["sensor"]["to_world"] = Transform4f().look_at([0, 0.2, 0], [0, 1, 0], [0, 0, 1])   # outside both spheres
+    d["sensor"]["fov"] = 10.0
+    d["integrator"]["max_depth"] = 1
+    scene = mi.load_dict(d)
+    img = scene.integrator().render(scene, seed=0, spp=16)
+    assert np.allclose(img[8:-8, 8:-8], 1.0, atol=1e-5)
+
+
+def test_render_sharded_equals_unsharded():
+    desc = scenes.cbox_scene(48, 32)
+    scene = mi.Scene(desc)
+    rp = scene.integrator().render_params(scene)
+    dev = scene.device()
+    full, st = dev.render_path(rp, seed=2, spp=32)
+    parts = [dev.render_path(rp, seed=2, spp=32, sample_offset=g, sample_stride=4) for g in range(4)]
+    acc = sum(f.astype(np.float64) for f, _ in parts)
+    assert sum(s["paths"] for _, s in parts) == st["paths"] == 48 * 48 * 32
+    assert sum(s["rays"] for _, s in parts) == st["rays"]
+    assert np.allclose(acc, full, rtol=2e-4, atol=1e-5)
+
+
+def test_render_api_through_plugins():
+    """mi.load_dict(...) -> mi.render(scene): the public call a Mitsuba user makes."""
+    scene = mi.load_dict(scenes.cbox_scene_dict(32, 8))
+    img = mi.render(scene, spp=8, seed=1)
+    assert img.shape == (32, 32, 3) and np.isfinite(img).all() and img.max() > 0.5 and img.mean() > 1e-3
+    # red wall is on the +x side = image right (camera looks down -z with +x to its left... see sensor frame)
+    left, right = img[10:22, 1:4].mean((0, 1)), img[10:22, -4:-1].mean((0, 1))
+    assert (left[1] > left[0]) != (right[1] > right[0])          # one side is green-ish, the other red-ish
