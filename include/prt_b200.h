@@ -54,6 +54,11 @@ int prt_device_count(int *count);
 int prt_create(int device, prt_context **out);
 int prt_destroy(prt_context *);
 int prt_device_info(prt_context *, int *sm_count, int *cc_major, int *cc_minor, uint64_t *global_mem_bytes);
+/* Page-locked host memory for result buffers.  prt_acquire / prt_render_path detect a pinned destination and
+ * copy device -> host straight into it (per-angle slices overlapped with the kernel of the next angle);
+ * pageable destinations go through an internal pinned staging buffer + memcpy. */
+int prt_host_alloc(prt_context *, uint64_t bytes, void **out);
+int prt_host_free(prt_context *, void *ptr);
 
 /* ---- scene upload (replaces mi.load_dict / mi.load_file, USMain.py:257; Mitsuba builds Embree here) */
 int prt_scene_create(prt_context *, prt_scene **out);

@@ -25,7 +25,7 @@ QF_CONNECT_TO_TARGET = 1 << 4
 
 # every symbol include/prt_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "prt_last_error", "prt_version", "prt_device_count", "prt_create", "prt_destroy", "prt_device_info",
+    "prt_last_error", "prt_version", "prt_device_count", "prt_create", "prt_destroy", "prt_device_info", "prt_host_alloc", "prt_host_free",
     "prt_scene_create", "prt_scene_destroy", "prt_scene_add_material", "prt_scene_set_material_param",
     "prt_scene_add_primitive", "prt_scene_add_mesh", "prt_scene_commit", "prt_trace_closest", "prt_trace_occluded",
     "prt_ultra_bsdf_sample", "prt_acquire", "prt_acquire_dev", "prt_acquire_trace", "prt_render_path",
@@ -110,6 +110,8 @@ def load():
     L.prt_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.prt_destroy.argtypes = [vp]
     L.prt_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), u64p]
+    L.prt_host_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    L.prt_host_free.argtypes = [vp, vp]
     L.prt_scene_create.argtypes = [vp, C.POINTER(vp)]
     L.prt_scene_destroy.argtypes = [vp]
     L.prt_scene_add_material.argtypes = [vp, C.c_int, dp, dp, C.POINTER(C.c_int)]

@@ -10,6 +10,8 @@
 // deposits are fire-and-forget red.global.add.f32 into the L2-resident channel buffer.
 // Canonical path semantics: SURVEY.md Appendix F.  Line tags CI:n / CB:n cite the reference files.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "prt_internal.h"
 
@@ -22,13 +24,14 @@ struct AcqDev {
     DScene sc;
     float4 T0, T1, T2;  // sensor to_world rows
     float3 nT;          // normalize(T * (0,0,1))
-    float c, fs, pitch, two_pi_f, att_k, alpha_m, alpha_c, cos_c, max_len, n_rays, inv_spp;
+    float c, fs, pitch, two_pi_f, att_k, alpha_m, alpha_c, cos_c, cos_m, max_len, n_rays, inv_spp;
     int n_a, n_e, Tn, max_depth;
     unsigned qf;
     const float2 *sincos;  // [n_a] (sin theta, cos theta)
     uint64_t seed;
     uint32_t spp_total, s_offset, s_stride;
     uint64_t n_s, total;   // samples per (a,e) for this call, total paths of this call
+    int a_first, a_count;  // angle range of this LAUNCH (prt_acquire pipelines one launch per angle with its D2H slice)
     float *buf, *tx;
     unsigned long long *stats;  // {paths, segments, rays, deposits, misses}
 };
@@ -96,8 +99,15 @@ __device__ __forceinline__ bool segment(const AcqDev &P, const DPrim *prims, Pat
     ultra_bsdf_sample(wi, h.ng, h.ns, __ldg(&mat.p[0]), __ldg(&mat.p[1]), s1, s2, dir, pdf, a_resp, reflect);   // CI:175 / 338
     const float cos_theta = dot(h.ns, md);                                       // CI:176 / 340
     ps.amp *= a_resp * cos_theta * fmaxf(pdf, 1e-6f);                            // CI:177 / 341
-    const float al = fabsf(acosf(dot(P.nT, -sec)));                              // CI:124-126
-    const float w_i = al <= P.alpha_m ? 1.0f : (al <= P.alpha_c ? (P.alpha_c - al) / (P.alpha_c - P.alpha_m) : 0.0f);   // CI:128-133
+    // CI:124-133: alpha = |acos(dot)|; w_i = 1 (alpha <= alpha_m), linear ramp to 0 at alpha_c, else 0.  acos is
+    // monotone, so the two plateaus are decided on the cosine and acosf only runs on the ramp (rare: the aperture
+    // subtends a few degrees; the ramp is continuous at both ends, so an ulp-level tie is immaterial)
+    const float cdt = dot(P.nT, -sec);
+    float w_i = cdt >= P.cos_m ? 1.0f : 0.0f;
+    if (cdt < P.cos_m && cdt >= P.cos_c) {
+        const float al = fabsf(acosf(cdt));
+        w_i = al <= P.alpha_m ? 1.0f : (al <= P.alpha_c ? (P.alpha_c - al) / (P.alpha_c - P.alpha_m) : 0.0f);
+    }
     const float w_o = dot(ps.d, h.ns) / P.n_rays;                                // CI:118,184
     const float press = ps.atten * ps.amp * (w_i * w_o) * sinf(phase);           // CI:187 / 348
     const float kf = rintf(Ttot * P.fs);                                         // CI:191 / 351-352 (half-even)
@@ -144,24 +154,31 @@ template <bool TRIS>
 __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const AcqDev P) {
     __shared__ DPrim sprims[MAX_SMEM_PRIMS];
     const DPrim *prims = stage_prims(P.sc, sprims);
+    // sample-major launch order: consecutive lanes -> consecutive (angle, element) of this launch's angle range,
+    // same sample.  (ae, si) advance incrementally -- no 64-bit divisions in the loop.
+    const uint32_t n_ae = (uint32_t) P.a_count * (uint32_t) P.n_e;
+    const uint32_t ae0 = (uint32_t) P.a_first * (uint32_t) P.n_e;
     const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-    uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t n_ae = (uint64_t) P.n_a * (uint64_t) P.n_e;
+    const uint64_t j0 = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t d_ae = (uint32_t) (stride % n_ae), d_si = (uint32_t) (stride / n_ae);
+    uint32_t ae = (uint32_t) (j0 % n_ae);
+    uint64_t si = j0 / n_ae;
     // transmit-delay table, CI:87-94 / 254-257
-    if (P.tx && j < n_ae) {
-        float2 sc = __ldg(P.sincos + (int) (j / (uint64_t) P.n_e));
-        P.tx[j] = (elem_x(P, (int) (j % (uint64_t) P.n_e)) * sc.x) / P.c;
+    if (P.tx && j0 < n_ae) {
+        uint32_t g = ae0 + (uint32_t) j0;
+        float2 sc = __ldg(P.sincos + (int) (g / (uint32_t) P.n_e));
+        P.tx[g] = (elem_x(P, (int) (g % (uint32_t) P.n_e)) * sc.x) / P.c;
     }
     Counters cn = { 0, 0, 0, 0, 0 };
     PathState ps;
     bool live = false;
     for (;;) {
         if (!live) {
-            if (j >= P.total) break;
-            // sample-major launch order: consecutive lanes -> consecutive (angle, element), same sample
-            uint64_t ae = j % n_ae, si = j / n_ae;
-            init_path(P, ae, P.s_offset + (uint32_t) si * P.s_stride, ps);
-            j += stride;
+            if (si >= P.n_s) break;
+            init_path(P, (uint64_t) (ae0 + ae), P.s_offset + (uint32_t) si * P.s_stride, ps);
+            ae += d_ae;
+            si += d_si;
+            if (ae >= n_ae) { ae -= n_ae; si++; }
             cn.paths++;
             live = P.max_depth > 0;
             if (!live) continue;
@@ -227,6 +244,7 @@ static int fill_params(prt_scene *s, const prt_acq_params *p, uint64_t seed, uin
     P.alpha_m = (float) (p->main_beam_deg * M_PI / 180.0);
     P.alpha_c = (float) (p->cutoff_deg * M_PI / 180.0);
     P.cos_c = cosf(P.alpha_c);
+    P.cos_m = cosf(P.alpha_m);
     P.max_len = (float) p->max_path_len;
     P.n_rays = (float) (p->n_angles * p->n_elements);
     P.inv_spp = 1.0f / (float) spp_total;
@@ -242,6 +260,8 @@ static int fill_params(prt_scene *s, const prt_acq_params *p, uint64_t seed, uin
     P.s_stride = s_stride ? s_stride : 1;
     P.n_s = s_offset < spp_total ? ((uint64_t) spp_total - s_offset + P.s_stride - 1) / P.s_stride : 0;
     P.total = P.n_s * (uint64_t) p->n_angles * (uint64_t) p->n_elements;
+    P.a_first = 0;
+    P.a_count = p->n_angles;
     P.buf = nullptr;
     P.tx = nullptr;
     P.stats = nullptr;
@@ -255,8 +275,9 @@ static int launch_acquire(prt_context *c, const AcqDev &P, cudaStream_t st) {
     if (tris) PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acquire<true>, ACQ_THREADS, 0));
     else PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acquire<false>, ACQ_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
-    uint64_t want = (P.total + ACQ_THREADS - 1) / ACQ_THREADS;
-    uint64_t n_ae_blocks = ((uint64_t) P.n_a * P.n_e + ACQ_THREADS - 1) / ACQ_THREADS;
+    const uint64_t n_ae_l = (uint64_t) P.a_count * P.n_e;
+    uint64_t want = (P.n_s * n_ae_l + ACQ_THREADS - 1) / ACQ_THREADS;
+    uint64_t n_ae_blocks = (n_ae_l + ACQ_THREADS - 1) / ACQ_THREADS;
     if (want < n_ae_blocks) want = n_ae_blocks;  // the tx-delay table is written by the first n_a*n_e threads
     uint64_t grid = (uint64_t) c->sm_count * per_sm;
     if (grid > want) grid = want;
@@ -286,7 +307,21 @@ int prt_acquire_dev(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32
     P.buf = channel_buf_dev;
     P.tx = tx_delays_dev;
     P.stats = reinterpret_cast<unsigned long long *>(stats_dev);
-    return launch_acquire(s->ctx, P, st);
+    // One launch per steering angle.  With stride = grid * 256 a multiple of n_e, every thread then keeps ONE
+    // (angle, element) for all of its paths, so the lanes of a warp stay on 32 neighbouring elements of one angle
+    // however their paths regenerate; in a single launch over all angles the lanes drift onto different angles
+    // and the warp's rays decohere (measured on B200: ring 42.2 -> 26.5 ms, Sphere_Box intended 13.6 -> 10.3 ms).
+    // PRT_ACQ_SPLIT=0 restores the single launch.
+    static const bool split = [] { const char *e = getenv("PRT_ACQ_SPLIT"); return !(e && e[0] == '0'); }();
+    if (!split || p->n_angles == 1) return launch_acquire(s->ctx, P, st);
+    for (int a = 0; a < p->n_angles; a++) {
+        AcqDev Q = P;
+        Q.a_first = a;
+        Q.a_count = 1;
+        rc = launch_acquire(s->ctx, Q, st);
+        if (rc) return rc;
+    }
+    return PRT_OK;
 }
 
 int prt_acquire(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
@@ -313,24 +348,49 @@ int prt_acquire(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t s
     P.tx = c->aux_dev;
     P.stats = reinterpret_cast<unsigned long long *>(c->stats_dev);
     PRT_CUDA(cudaEventRecord(e1, st));
-    rc = launch_acquire(c, P, st);
-    if (rc) return rc;
-    PRT_CUDA(cudaEventRecord(e2, st));
-    // D2H through the pinned staging buffer, then into the caller's (pageable) arrays
+    // Is the destination page-locked (prt_host_alloc / cudaHostRegister)?  Then copy straight into it, one angle
+    // slice at a time on the copy stream while the next angle's paths are still being traced.
+    cudaPointerAttributes attr;
+    bool pinned_dst = cudaPointerGetAttributes(&attr, channel_buf) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
     float *pin = reinterpret_cast<float *>(c->pinned);
-    PRT_CUDA(cudaMemcpyAsync(pin, c->acc_dev, sizeof(float) * n_buf, cudaMemcpyDeviceToHost, st));
+    unsigned launches = 0;
+    if (pinned_dst && p->n_angles > 1) {
+        const size_t slice = (size_t) p->n_elements * (size_t) p->time_samples;
+        for (int a = 0; a < p->n_angles; a++) {
+            AcqDev Q = P;
+            Q.a_first = a;
+            Q.a_count = 1;
+            rc = launch_acquire(c, Q, st);
+            if (rc) return rc;
+            launches++;
+            PRT_CUDA(cudaEventRecord(c->slice_done[a & 1], st));
+            PRT_CUDA(cudaStreamWaitEvent(c->copy_stream, c->slice_done[a & 1], 0));
+            PRT_CUDA(cudaMemcpyAsync(channel_buf + a * slice, c->acc_dev + a * slice, sizeof(float) * slice, cudaMemcpyDeviceToHost,
+                                     c->copy_stream));
+        }
+        PRT_CUDA(cudaEventRecord(e2, st));
+        PRT_CUDA(cudaEventRecord(c->slice_done[0], c->copy_stream));
+        PRT_CUDA(cudaStreamWaitEvent(st, c->slice_done[0], 0));
+    } else {
+        rc = launch_acquire(c, P, st);
+        if (rc) return rc;
+        launches = 1;
+        PRT_CUDA(cudaEventRecord(e2, st));
+        PRT_CUDA(cudaMemcpyAsync(pinned_dst ? channel_buf : pin, c->acc_dev, sizeof(float) * n_buf, cudaMemcpyDeviceToHost, st));
+    }
     PRT_CUDA(cudaMemcpyAsync(pin + n_buf, c->aux_dev, sizeof(float) * n_tx, cudaMemcpyDeviceToHost, st));
     uint64_t hs[8];
     PRT_CUDA(cudaMemcpyAsync(hs, c->stats_dev, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
     PRT_CUDA(cudaEventRecord(e3, st));
     PRT_CUDA(cudaStreamSynchronize(st));
-    memcpy(channel_buf, pin, sizeof(float) * n_buf);
+    if (!pinned_dst) memcpy(channel_buf, pin, sizeof(float) * n_buf);
     if (tx_delays) memcpy(tx_delays, pin + n_buf, sizeof(float) * n_tx);
     if (stats) {
         stats->paths = hs[0]; stats->segments = hs[1]; stats->rays = hs[2]; stats->deposits = hs[3]; stats->misses = hs[4];
         PRT_CUDA(cudaEventElapsedTime(&stats->kernel_ms, e1, e2));
         PRT_CUDA(cudaEventElapsedTime(&stats->total_ms, e0, e3));
-        stats->launches = 1;
+        stats->launches = launches;
         stats->_pad = 0;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);

@@ -303,9 +303,11 @@ __device__ __forceinline__ bool intersect_tri_wt(const RayPre &rp, float3 o, flo
                                                  float &b1, float &b2) {
     float3 A = v0 - o, B = v1 - o, C = v2 - o;
     float Akz = comp(A, rp.kz), Bkz = comp(B, rp.kz), Ckz = comp(C, rp.kz);
-    float Ax = __fsub_rn(comp(A, rp.kx), __fmul_rn(rp.Sx, Akz)), Ay = __fsub_rn(comp(A, rp.ky), __fmul_rn(rp.Sy, Akz));
-    float Bx = __fsub_rn(comp(B, rp.kx), __fmul_rn(rp.Sx, Bkz)), By = __fsub_rn(comp(B, rp.ky), __fmul_rn(rp.Sy, Bkz));
-    float Cx = __fsub_rn(comp(C, rp.kx), __fmul_rn(rp.Sx, Ckz)), Cy = __fsub_rn(comp(C, rp.ky), __fmul_rn(rp.Sy, Ckz));
+    // shear: a function of (vertex, ray) only, so a vertex shared by two triangles maps to the same point whether
+    // or not the multiply-add is fused -- fusing it is safe; the EDGE functions below must stay un-fused
+    float Ax = fmaf(-rp.Sx, Akz, comp(A, rp.kx)), Ay = fmaf(-rp.Sy, Akz, comp(A, rp.ky));
+    float Bx = fmaf(-rp.Sx, Bkz, comp(B, rp.kx)), By = fmaf(-rp.Sy, Bkz, comp(B, rp.ky));
+    float Cx = fmaf(-rp.Sx, Ckz, comp(C, rp.kx)), Cy = fmaf(-rp.Sy, Ckz, comp(C, rp.ky));
     float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
     float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
     float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));

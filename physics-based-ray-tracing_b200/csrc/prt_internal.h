@@ -44,6 +44,8 @@ struct prt_context {
     cudaDeviceProp prop;
     std::mutex mtx;
     cudaStream_t stream;          // library-owned stream for the host-buffer entry points
+    cudaStream_t copy_stream;     // D2H of finished result slices, overlapped with the next launch
+    cudaEvent_t  slice_done[2];
     // scratch for the acquisition / render entry points (grown on demand, reused across calls)
     float    *acc_dev;   size_t acc_cap;      // accumulator (channel_buf / film)
     float    *aux_dev;   size_t aux_cap;      // tx_delays etc.

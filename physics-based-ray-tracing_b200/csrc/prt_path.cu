@@ -419,12 +419,16 @@ int prt_render_path(prt_scene *s, const prt_render_params *p, uint64_t seed, uin
     if (rc) return rc;
     PRT_CUDA(cudaEventRecord(e2, st));
     float *pin = reinterpret_cast<float *>(c->pinned);
+    cudaPointerAttributes attr;
+    const bool pinned_dst = cudaPointerGetAttributes(&attr, film_rgbw) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned_dst) pin = film_rgbw;
     PRT_CUDA(cudaMemcpyAsync(pin, c->acc_dev, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     uint64_t hs[8];
     PRT_CUDA(cudaMemcpyAsync(hs, c->stats_dev, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
     PRT_CUDA(cudaEventRecord(e3, st));
     PRT_CUDA(cudaStreamSynchronize(st));
-    memcpy(film_rgbw, pin, sizeof(float) * n);
+    if (!pinned_dst) memcpy(film_rgbw, pin, sizeof(float) * n);
     if (stats) {
         stats->paths = hs[0]; stats->segments = hs[1]; stats->rays = hs[2]; stats->shadow_rays = hs[3];
         PRT_CUDA(cudaEventElapsedTime(&stats->kernel_ms, e1, e2));

@@ -131,6 +131,9 @@ int prt_create(int device, prt_context **out) {
     c->pinned_cap = 0;
     c->stats_dev = nullptr;
     PRT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PRT_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    PRT_CUDA(cudaEventCreateWithFlags(&c->slice_done[0], cudaEventDisableTiming));
+    PRT_CUDA(cudaEventCreateWithFlags(&c->slice_done[1], cudaEventDisableTiming));
     PRT_CUDA(cudaMalloc(&c->stats_dev, sizeof(uint64_t) * 8));
     *out = c;
     return PRT_OK;
@@ -145,6 +148,9 @@ int prt_destroy(prt_context *c) {
     if (c->stats_dev) cudaFree(c->stats_dev);
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->slice_done[0]);
+    cudaEventDestroy(c->slice_done[1]);
     delete c;
     return PRT_OK;
 }
@@ -155,6 +161,20 @@ int prt_device_info(prt_context *c, int *sm_count, int *cc_major, int *cc_minor,
     if (cc_major) *cc_major = c->prop.major;
     if (cc_minor) *cc_minor = c->prop.minor;
     if (global_mem_bytes) *global_mem_bytes = (uint64_t) c->prop.totalGlobalMem;
+    return PRT_OK;
+}
+
+int prt_host_alloc(prt_context *c, uint64_t bytes, void **out) {
+    PRT_REQUIRE(c && out && bytes > 0, "prt_host_alloc: invalid argument");
+    *out = nullptr;
+    PRT_CUDA(cudaSetDevice(c->device));
+    PRT_CUDA(cudaHostAlloc(out, (size_t) bytes, cudaHostAllocPortable));
+    return PRT_OK;
+}
+
+int prt_host_free(prt_context *c, void *ptr) {
+    PRT_REQUIRE(c, "prt_host_free: null context");
+    if (ptr) PRT_CUDA(cudaFreeHost(ptr));
     return PRT_OK;
 }
 

@@ -35,6 +35,27 @@ class Context:
         check(self.L.prt_device_info(h, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem)))
         self.sm_count, self.cc, self.global_mem = sm.value, (maj.value, mnr.value), mem.value
 
+    def pinned_array(self, shape, dtype=np.float32) -> np.ndarray:
+        """A page-locked numpy array (prt_host_alloc) for a result: D2H goes straight into it -- no staging memcpy,
+        no page faults on a fresh allocation.  Buffers are pooled per shape and a buffer is handed out again only
+        once NO numpy view of it is alive any more: every view (and every view derived from one: numpy collapses
+        ``.base`` chains onto the pool's array) holds a reference to the pool's array, so its refcount tells.  A
+        result the caller still holds is therefore never overwritten; the pool grows instead."""
+        import sys
+        key = (tuple(shape), np.dtype(dtype).str)
+        pool = self.__dict__.setdefault("_pinned", {}).setdefault(key, [])
+        for k in range(len(pool)):
+            if sys.getrefcount(pool[k][0]) == pool[k][1]:
+                return pool[k][0].reshape(shape)
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        check(self.L.prt_host_alloc(self.h, nbytes, C.byref(ptr)), "prt_host_alloc")
+        raw = (C.c_byte * nbytes).from_address(ptr.value)
+        pool.append([np.frombuffer(raw, dtype=dtype), 0])     # the array every hand-out's .base collapses onto
+        k = len(pool) - 1
+        pool[k][1] = sys.getrefcount(pool[k][0])          # idle refcount, measured the same way as above
+        return pool[k][0].reshape(shape)
+
     @staticmethod
     def get(device: Optional[int] = None) -> "Context":
         if device is None:
@@ -129,7 +150,7 @@ class DeviceScene:
     def acquire(self, params: AcqParams, seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1):
         """Host-buffer entry point: returns (channel_buf [n_a,n_e,T] f32, tx_delays [n_a,n_e] f32, stats)."""
         ps = capi.make_acq_params(params)
-        buf = np.empty((params.n_angles, params.n_elements, params.time_samples), dtype=np.float32)
+        buf = self.ctx.pinned_array((params.n_angles, params.n_elements, params.time_samples), np.float32)
         tx = np.empty((params.n_angles, params.n_elements), dtype=np.float32)
         st = capi.AcqStatsC()
         check(self.L.prt_acquire(self.h, C.byref(ps), seed, spp, sample_offset, sample_stride, fptr(buf), fptr(tx),
@@ -154,7 +175,7 @@ class DeviceScene:
 
     # -- mi.render with the `path` integrator ------------------------------------------------------
     def render_path(self, rp: "capi.RenderParamsC", seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1):
-        film = np.empty((rp.height, rp.width, 4), dtype=np.float32)
+        film = self.ctx.pinned_array((rp.height, rp.width, 4), np.float32)
         st = capi.RenderStatsC()
         check(self.L.prt_render_path(self.h, C.byref(rp), seed, spp, sample_offset, sample_stride, fptr(film), C.byref(st)),
               "prt_render_path")
