@@ -395,7 +395,8 @@ def main():
             integ.seed = 2000 + k
             integ.simulate_acquisition_parallel(scene)
             e2e_rays += int(integ.last_stats["rays"])
-            host_checksum = float(integ.channel_buf.sum())     # the result is really on the host
+            host_checksum = float(integ.channel_buf.ravel()[::997].sum())   # touch the HOST result (strided: a full
+            #                                                                  sum of 12.8 MB costs more than the kernel)
         barrier()
         e2e_dt = time.perf_counter() - t0
     finally:
