@@ -132,19 +132,30 @@ def run_pt(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    res = args.res
-    spp_step = args.spp if args.spp != C2_SPP else 16
-    desc = scenes.cbox_scene(res, spp_step)
+    if args.workload.startswith("heightfield"):
+        # BASELINE config 5: 9 999 392-triangle height field in a closed box, 3840x2160, 8 diffuse bounces, no RR
+        n_side = int(args.workload.partition(":")[2] or 2237)
+        width, height = (3840, 2160) if args.res == 2048 else (args.res, args.res * 9 // 16)
+        spp_step = args.spp if args.spp != C2_SPP else 2
+        desc = scenes.heightfield_scene(n_side, (width, height), spp_step)
+        wl_label = (f"synthetic height field, {desc.n_triangles()} triangles in a closed box, {width}x{height}, all diffuse, "
+                    "8 bounces (max_depth 9), no RR")
+    else:
+        width = height = args.res
+        spp_step = args.spp if args.spp != C2_SPP else 16
+        desc = scenes.cbox_scene(args.res, spp_step)
+        wl_label = f"scenes/cbox.xml at {width}x{height}, path integrator max_depth 6 rr_depth 5, tent filter"
     scene = mi.Scene(desc)
     integ = scene.integrator()
     dev = scene.device()
     rp = integ.render_params(scene)
     spp_total = spp_step * world
     off, stride, n_s = shard_samples(spp_total, rank, world)
-    film = torch.zeros((res, res, 4), dtype=torch.float32, device=device)
+    film = torch.zeros((height, width, 4), dtype=torch.float32, device=device)
     stats = torch.zeros(8, dtype=torch.int64, device=device)
     flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=device)
     stream = torch.cuda.current_stream(device)
+    bvh = dev.bvh_stats
 
     def barrier():
         if world > 1:
@@ -215,8 +226,10 @@ def run_pt(args, rank, world, local_rank):
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "msamples_per_s": paths / (total_ms * 1e-3) / 1e6,
-                "config": {"workload": f"scenes/cbox.xml at {res}x{res}, path integrator max_depth 6 rr_depth 5, tent filter",
-                           "spp_per_gpu_per_step": spp_step, "paths_per_gpu_per_step": res * res * n_s, "n_triangles": n_tris,
+                "config": {"workload": wl_label,
+                           "spp_per_gpu_per_step": spp_step, "paths_per_gpu_per_step": width * height * n_s, "n_triangles": n_tris,
+                           "bvh": {"nodes": bvh["n_nodes"], "build_ms": bvh["build_ms"], "sah_cost": bvh["sah_cost"],
+                                   "device_bytes": bvh["device_bytes"]},
                            "n_analytic": desc.n_analytic(), "segments_per_path": segments / max(paths, 1),
                            "rays_per_path": rays / max(paths, 1),
                            "parallelism": f"sample-shards x{world}, BVH replicated, 1 NCCL all-reduce of {film.numel() * 4} B",
@@ -227,9 +240,10 @@ def run_pt(args, rank, world, local_rank):
                 "gpu_launches": args.steps, "kernel": "prt::k_render_path", "kernel_ms": kern_ms,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                             "note": "B_min(12 tris) = 368 B/ray of node+triangle fetches, all served on chip (scene < 2 KB)"},
+                             "note": f"B_min(N) = {bvh_min_bytes(n_tris)} B/ray of node + triangle fetches (SURVEY 8(d)); "
+                                     + ("scene lives on chip" if n_tris < 100000 else "scene >> L2: fetches go to HBM")},
                 "clocks": clk}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.workload.startswith("heightfield"):
             import orc_py
             threads = os.cpu_count() or 1
             cres, cspp = 256, 16                      # the cbox tutorial resolution, 16 spp: ~1 M paths
@@ -296,7 +310,7 @@ def main():
         run_reference(args, rank)
         return
     args.warmup = max(args.warmup, 3)
-    if args.workload == "cbox":
+    if args.workload == "cbox" or args.workload.startswith("heightfield"):
         run_pt(args, rank, world, local_rank)
         return
 

@@ -220,23 +220,24 @@ def cbox_scene(res: int = 256, spp: int = 128, max_depth: int = 6) -> SceneDesc:
 
 
 def heightfield_scene_dict(n: int = 2237, res=(3840, 2160), spp: int = 64) -> dict:
-    """BASELINE.json config 5: closed box, ceiling light quad, height-field floor of
-    2 (n-1)^2 triangles, all diffuse 0.5, exactly 8 bounces (max_depth 9, rr disabled by the caller)."""
+    """BASELINE.json config 5: closed box x,z in [-1,1], y in [-1.2,1], ceiling light quad,
+    floor = height field of 2 (n-1)^2 triangles (n = 2237 -> 9 999 392) around y = -1, all diffuse 0.5, exactly
+    8 bounces (max_depth 9, Russian roulette disabled), camera inside the box looking down at the floor."""
     v, _, idx = heightfield_mesh(n)
-    # height field z -> world y (floor), lifted to y = -1
-    floor = {"type": "mesh", "vertices": np.stack([v[:, 0], v[:, 2] - 1.0, -v[:, 1]], axis=1), "normals": None,
-             "faces": idx, "bsdf": {"type": "ref", "id": "grey"}}
+    # height field z -> world y (floor), lifted to y = -1; flip winding so the face normals point up (+y)
+    floor = {"type": "mesh", "vertices": np.stack([v[:, 0], v[:, 2] - 1.0, v[:, 1]], axis=1), "normals": None,
+             "faces": idx[:, ::-1].copy(), "bsdf": {"type": "ref", "id": "grey"}}
     d = {
         "type": "scene", "integrator": {"type": "path", "max_depth": 9, "rr_depth": 1000},
         "sensor": {"type": "perspective", "fov_axis": "smaller", "near_clip": 0.001, "far_clip": 100.0, "fov": 39.3077,
-                   "to_world": T().look_at([0, 0.2, 3.8], [0, -0.4, 0], [0, 1, 0]),
+                   "to_world": T().look_at([0, 0.3, 0.95], [0, -0.9, -0.2], [0, 1, 0]),
                    "sampler": {"type": "independent", "sample_count": spp},
                    "film": {"type": "hdrfilm", "width": res[0], "height": res[1], "rfilter": {"type": "tent"}}},
         "grey": {"type": "diffuse", "reflectance": [0.5, 0.5, 0.5]},
         "floor": floor,
     }
     ref = {"type": "ref", "id": "grey"}
-    walls = {
+    walls = {   # inward-facing quads
         "ceiling": [(1, 1, -1), (1, 1, 1), (-1, 1, 1), (-1, 1, -1)],
         "back": [(1, -1.2, -1), (1, 1, -1), (-1, 1, -1), (-1, -1.2, -1)],
         "left": [(-1, 1, -1), (-1, 1, 1), (-1, -1.2, 1), (-1, -1.2, -1)],
@@ -251,3 +252,9 @@ def heightfield_scene_dict(n: int = 2237, res=(3840, 2160), spp: int = 64) -> di
     light.update({"bsdf": ref, "emitter": {"type": "area", "radiance": [10.0, 10.0, 10.0]}})
     d["light"] = light
     return d
+
+
+def heightfield_scene(n: int = 2237, res=(3840, 2160), spp: int = 64) -> SceneDesc:
+    desc = load_dict_desc(heightfield_scene_dict(n, res, spp))
+    desc.source = f"<builtin:heightfield:{n}>"
+    return desc

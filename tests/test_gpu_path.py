@@ -81,3 +81,34 @@ def test_render_api_through_plugins():
     # red wall is on the +x side = image right (camera looks down -z with +x to its left... see sensor frame)
     left, right = img[10:22, 1:4].mean((0, 1)), img[10:22, -4:-1].mean((0, 1))
     assert (left[1] > left[0]) != (right[1] > right[0])          # one side is green-ish, the other red-ish
+
+
+def test_heightfield_lbvh_against_oracle(orc):
+    """A 79 214-triangle height field in a box (the small sibling of BASELINE config 5): GPU LBVH hits vs the
+    oracle's own BVH on random rays, and the 8-bounce diffuse image on the same seeds."""
+    desc = scenes.heightfield_scene(200, (64, 36), 8)
+    scene = mi.Scene(desc)
+    dev = scene.device()
+    st = dev.bvh_stats
+    assert st["n_triangles"] == 2 * 199 * 199 + 12 and st["n_nodes"] == st["n_triangles"] - 1
+    rng = np.random.default_rng(4)
+    o = rng.uniform((-0.9, -0.8, -0.9), (0.9, 0.9, 0.9), size=(40000, 3)).astype(np.float32)
+    d = rng.normal(size=(40000, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(np.float32)
+    g = dev.trace_closest(o, d)
+    osc = orc.OracleScene(desc)
+    c = osc.trace_closest(o, d, prec=32)
+    c64 = osc.trace_closest(o, d, prec=64)
+    assert (g["prim"] >= 0).all()                                     # closed box: no ray escapes (watertight)
+    same = g["prim"] == c["prim"]
+    assert same.mean() > 0.998
+    cosv = np.abs(np.sum(d.astype(np.float64) * c64["ng"], axis=1))
+    ok = same & (c64["prim"] == c["prim"]) & (cosv > 0.05)
+    err = np.abs(g["t"][ok].astype(np.float64) - c64["t"][ok])
+    assert (err <= 1e-5 * c64["t"][ok] + 5e-7).all()
+    rp = scene.integrator().render_params(scene)
+    film, fst = dev.render_path(rp, seed=1, spp=8)
+    ref, rst = orc.render_path(osc, rp, seed=1, spp=8, prec=32)
+    assert fst["paths"] == rst["paths"] and abs(fst["segments"] - rst["segments"]) <= 2e-3 * rst["segments"]
+    gi, ci = _image(film), _image(ref)
+    assert _rel_mse(gi, ci) < 1e-3
