@@ -173,6 +173,8 @@ typedef struct {
  * envelope [nx][nz] f32 (magnitude of the analytic signal along z) */
 int prt_das_beamform(prt_context *, const prt_das_params *, const float *channel, const float *tx_delays,
                      const double *angles_deg, const float *x, const float *z, float *rf, float *envelope);
+/* envelope of an already beamformed image rf [nx][nz] (DelayAndSum.compute_envelope, USMain.py:208) */
+int prt_envelope(prt_context *, const float *rf, int32_t nx, int32_t nz, float *envelope);
 
 #ifdef __cplusplus
 }

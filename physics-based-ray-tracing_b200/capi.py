@@ -29,7 +29,7 @@ EXPORTS = [
     "prt_scene_create", "prt_scene_destroy", "prt_scene_add_material", "prt_scene_set_material_param",
     "prt_scene_add_primitive", "prt_scene_add_mesh", "prt_scene_commit", "prt_trace_closest", "prt_trace_occluded",
     "prt_ultra_bsdf_sample", "prt_acquire", "prt_acquire_dev", "prt_acquire_trace", "prt_render_path",
-    "prt_render_path_dev", "prt_das_beamform",
+    "prt_render_path_dev", "prt_das_beamform", "prt_envelope",
 ]
 
 
@@ -130,6 +130,7 @@ def load():
                                   C.POINTER(RenderStatsC)]
     L.prt_render_path_dev.argtypes = [vp, C.POINTER(RenderParamsC), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.prt_das_beamform.argtypes = [vp, C.POINTER(DasParamsC), fp, fp, dp, fp, fp, fp, fp]
+    L.prt_envelope.argtypes = [vp, fp, C.c_int32, C.c_int32, fp]
     _lib = L
     return L
 

@@ -1,0 +1,166 @@
+// prt_das.cu -- "next" row f1: plane-wave delay-and-sum beamformer + envelope detection,
+// the stage that consumes channel_buf in every us_render() of the reference driver
+// (/root/reference/USMain.py:129-208: ultraspy DelayAndSum(on_gpu=False).beamform + compute_envelope, a CPU
+// library that is neither vendored nor installable here).  Published algorithm restated: for every pixel (x, z),
+// every steering angle a and receive element e,
+//     tau = (z cos(theta_a) + x sin(theta_a)) / c  +  sqrt((x - x_e)^2 + z^2) / c  -  t0
+// the RF sample at tau * fs is linearly interpolated, weighted by a boxcar f-number aperture and summed;
+// compounding averages over angles.  The envelope is the magnitude of the analytic signal along z, computed per
+// image column with a direct O(N^2) DFT in shared memory (N = 638 at the driver's grid: cheaper than a launch
+// of a general FFT and free of library dependencies).
+#include <cmath>
+
+#include "prt_internal.h"
+
+namespace prt {
+
+struct DasDev {
+    int n_a, n_e, T, nx, nz;
+    float fs, inv_c, pitch, t0, f_number;
+    const float *channel, *x, *z;
+    const float2 *sincos;
+    float *rf;
+};
+
+__global__ void __launch_bounds__(256) k_das(const DasDev P) {
+    // one thread per pixel; threads of a warp walk along z (neighbouring samples of the same channel row)
+    int iz = blockIdx.x * blockDim.x + threadIdx.x, ix = blockIdx.y;
+    if (iz >= P.nz) return;
+    const float x = __ldg(P.x + ix), z = __ldg(P.z + iz);
+    float acc = 0.0f;
+    for (int a = 0; a < P.n_a; a++) {
+        const float2 sc = __ldg(P.sincos + a);
+        const float t_tx = fmaf(z, sc.y, x * sc.x) * P.inv_c;
+        float sum = 0.0f;
+        const float *rows = P.channel + (size_t) a * P.n_e * P.T;
+        for (int e = 0; e < P.n_e; e++) {
+            const float xe = P.pitch * ((float) e - (float) (P.n_e - 1) * 0.5f);
+            const float dx = x - xe;
+            // boxcar aperture: |dx| <= z / (2 f#)
+            if (P.f_number > 0.0f && fabsf(dx) * 2.0f * P.f_number > z) continue;
+            const float t = t_tx + sqrtf(fmaf(dx, dx, z * z)) * P.inv_c - P.t0;
+            const float s = t * P.fs;
+            const int i0 = (int) floorf(s);
+            if (i0 < 0 || i0 + 1 >= P.T) continue;
+            const float w = s - (float) i0;
+            const float *r = rows + (size_t) e * P.T + i0;
+            sum += fmaf(w, __ldg(r + 1) - __ldg(r), __ldg(r));
+        }
+        acc += sum;
+    }
+    P.rf[(size_t) ix * P.nz + iz] = acc / (float) P.n_a;
+}
+
+// analytic signal along z for one column per CTA: X[k] = sum x[n] e^{-2 pi i k n / N}; keep k = 0 (and N/2),
+// double 0 < k < N/2, drop the rest; envelope[n] = |sum_k H[k] X[k] e^{+2 pi i k n / N}| / N
+__global__ void __launch_bounds__(256) k_envelope(const float *__restrict__ rf, float *__restrict__ env, int nx, int nz) {
+    extern __shared__ float sm[];
+    float *xs = sm;                 // [nz]
+    float2 *X = (float2 *) (sm + ((nz + 1) & ~1));   // [nz]
+    const int ix = blockIdx.x;
+    for (int n = threadIdx.x; n < nz; n += blockDim.x) xs[n] = rf[(size_t) ix * nz + n];
+    __syncthreads();
+    const float w0 = -2.0f / (float) nz;
+    for (int k = threadIdx.x; k < nz; k += blockDim.x) {
+        float re = 0.0f, im = 0.0f;
+        for (int n = 0; n < nz; n++) {
+            float s, c;
+            sincospif(w0 * (float) ((long long) k * n % nz), &s, &c);
+            re = fmaf(xs[n], c, re);
+            im = fmaf(xs[n], s, im);
+        }
+        float h = (k == 0 || (nz % 2 == 0 && k == nz / 2)) ? 1.0f : (k < (nz + 1) / 2 ? 2.0f : 0.0f);
+        X[k] = make_float2(re * h, im * h);
+    }
+    __syncthreads();
+    const float w1 = 2.0f / (float) nz;
+    const int kmax = nz / 2 + 1;    // the rest is zero
+    for (int n = threadIdx.x; n < nz; n += blockDim.x) {
+        float re = 0.0f, im = 0.0f;
+        for (int k = 0; k < kmax; k++) {
+            float s, c;
+            sincospif(w1 * (float) ((long long) k * n % nz), &s, &c);
+            float2 v = X[k];
+            re += v.x * c - v.y * s;
+            im += v.x * s + v.y * c;
+        }
+        env[(size_t) ix * nz + n] = sqrtf(re * re + im * im) / (float) nz;
+    }
+}
+
+}  // namespace prt
+
+using namespace prt;
+
+extern "C" int prt_das_beamform(prt_context *c, const prt_das_params *p, const float *channel, const float *tx_delays,
+                                const double *angles_deg, const float *x, const float *z, float *rf, float *envelope) {
+    PRT_REQUIRE(c && p && channel && angles_deg && x && z && (rf || envelope), "prt_das_beamform: null argument");
+    PRT_REQUIRE(p->n_angles > 0 && p->n_elements > 0 && p->time_samples > 1 && p->nx > 0 && p->nz > 0 && p->fs > 0 && p->sound_speed > 0,
+                "prt_das_beamform: invalid parameters");
+    PRT_REQUIRE(p->nz <= 8192, "prt_das_beamform: nz too large for the in-shared-memory envelope (limit 8192)");
+    (void) tx_delays;   // plane-wave delays are x_e sin(theta)/c by construction (CustomIntegrator.py:87); angles are authoritative
+    std::lock_guard<std::mutex> lk(c->mtx);
+    PRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t n_ch = (size_t) p->n_angles * p->n_elements * p->time_samples, n_px = (size_t) p->nx * p->nz;
+    float *ch_d = nullptr, *x_d = nullptr, *z_d = nullptr, *rf_d = nullptr, *env_d = nullptr;
+    float2 *sc_d = nullptr;
+    std::vector<float2> sc(p->n_angles);
+    for (int a = 0; a < p->n_angles; a++) {
+        double th = angles_deg[a] * M_PI / 180.0;
+        sc[a] = make_float2((float) std::sin(th), (float) std::cos(th));
+    }
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    ok(cudaMalloc(&ch_d, sizeof(float) * n_ch)) && ok(cudaMalloc(&x_d, sizeof(float) * p->nx)) && ok(cudaMalloc(&z_d, sizeof(float) * p->nz)) &&
+        ok(cudaMalloc(&rf_d, sizeof(float) * n_px)) && ok(cudaMalloc(&env_d, sizeof(float) * n_px)) && ok(cudaMalloc(&sc_d, sizeof(float2) * p->n_angles));
+    if (e == cudaSuccess) {
+        ok(cudaMemcpyAsync(ch_d, channel, sizeof(float) * n_ch, cudaMemcpyHostToDevice, st));
+        ok(cudaMemcpyAsync(x_d, x, sizeof(float) * p->nx, cudaMemcpyHostToDevice, st));
+        ok(cudaMemcpyAsync(z_d, z, sizeof(float) * p->nz, cudaMemcpyHostToDevice, st));
+        ok(cudaMemcpyAsync(sc_d, sc.data(), sizeof(float2) * p->n_angles, cudaMemcpyHostToDevice, st));
+        DasDev P;
+        P.n_a = p->n_angles; P.n_e = p->n_elements; P.T = p->time_samples; P.nx = p->nx; P.nz = p->nz;
+        P.fs = (float) p->fs; P.inv_c = (float) (1.0 / p->sound_speed); P.pitch = (float) p->pitch; P.t0 = (float) p->t0;
+        P.f_number = (float) p->f_number;
+        P.channel = ch_d; P.x = x_d; P.z = z_d; P.sincos = sc_d; P.rf = rf_d;
+        dim3 grid((p->nz + 255) / 256, p->nx);
+        k_das<<<grid, 256, 0, st>>>(P);
+        size_t smem = sizeof(float) * ((p->nz + 1) & ~1) + sizeof(float2) * p->nz;
+        if (smem > 48 * 1024) ok(cudaFuncSetAttribute(k_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        k_envelope<<<p->nx, 256, smem, st>>>(rf_d, env_d, p->nx, p->nz);
+        ok(cudaGetLastError());
+        if (rf) ok(cudaMemcpyAsync(rf, rf_d, sizeof(float) * n_px, cudaMemcpyDeviceToHost, st));
+        if (envelope) ok(cudaMemcpyAsync(envelope, env_d, sizeof(float) * n_px, cudaMemcpyDeviceToHost, st));
+        ok(cudaStreamSynchronize(st));
+    }
+    cudaFree(ch_d); cudaFree(x_d); cudaFree(z_d); cudaFree(rf_d); cudaFree(env_d); cudaFree(sc_d);
+    PRT_CUDA(e);
+    return PRT_OK;
+}
+
+extern "C" int prt_envelope(prt_context *c, const float *rf, int32_t nx, int32_t nz, float *envelope) {
+    PRT_REQUIRE(c && rf && envelope && nx > 0 && nz > 0 && nz <= 8192, "prt_envelope: invalid argument");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    PRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t n_px = (size_t) nx * nz;
+    float *rf_d = nullptr, *env_d = nullptr;
+    cudaError_t e = cudaMalloc(&rf_d, sizeof(float) * n_px);
+    if (e == cudaSuccess) e = cudaMalloc(&env_d, sizeof(float) * n_px);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rf_d, rf, sizeof(float) * n_px, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        size_t smem = sizeof(float) * ((nz + 1) & ~1) + sizeof(float2) * nz;
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e == cudaSuccess) {
+            k_envelope<<<nx, 256, smem, st>>>(rf_d, env_d, nx, nz);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(envelope, env_d, sizeof(float) * n_px, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(rf_d);
+    cudaFree(env_d);
+    PRT_CUDA(e);
+    return PRT_OK;
+}

@@ -205,3 +205,32 @@ def ultra_bsdf_sample(wi, ng, ns, impedance, roughness, s1, s2, context: Optiona
     check(ctx.L.prt_ultra_bsdf_sample(ctx.h, n, fptr(wi), fptr(ng), fptr(ns), fptr(z), fptr(r), fptr(a), fptr(b), fptr(d),
                                       fptr(pdf), fptr(amp), rf.ctypes.data_as(C.POINTER(C.c_int32))), "prt_ultra_bsdf_sample")
     return d, pdf, amp, rf.astype(bool)
+
+
+def das_beamform(channel, angles_deg, x, z, fs, sound_speed, pitch, t0=0.0, f_number=0.0, tx_delays=None,
+                 context: Optional[Context] = None):
+    """Plane-wave delay-and-sum + envelope on the GPU (replaces ultraspy's DelayAndSum, USMain.py:175-208).
+    channel [n_a, n_e, T] f32 -> (rf [nx, nz], envelope [nx, nz])."""
+    ctx = context or Context.get()
+    ch = np.ascontiguousarray(channel, dtype=np.float32)
+    n_a, n_e, T = ch.shape
+    xs = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    zs = np.ascontiguousarray(z, dtype=np.float32).reshape(-1)
+    ang = np.ascontiguousarray(angles_deg, dtype=np.float64).reshape(-1)
+    if ang.size != n_a:
+        raise ValueError("das_beamform: one angle per transmission expected")
+    p = capi.DasParamsC(n_a, n_e, T, xs.size, zs.size, float(fs), float(sound_speed), float(pitch), float(t0), float(f_number))
+    txd = None if tx_delays is None else np.ascontiguousarray(tx_delays, dtype=np.float32)
+    rf = np.empty((xs.size, zs.size), dtype=np.float32)
+    env = np.empty((xs.size, zs.size), dtype=np.float32)
+    check(ctx.L.prt_das_beamform(ctx.h, C.byref(p), fptr(ch), fptr(txd), dptr(ang), fptr(xs), fptr(zs), fptr(rf), fptr(env)),
+          "prt_das_beamform")
+    return rf, env
+
+
+def envelope(rf, context: Optional[Context] = None):
+    ctx = context or Context.get()
+    r = np.ascontiguousarray(rf, dtype=np.float32)
+    env = np.empty_like(r)
+    check(ctx.L.prt_envelope(ctx.h, fptr(r), r.shape[0], r.shape[1], fptr(env)), "prt_envelope")
+    return env

@@ -1,0 +1,127 @@
+"""GPU: the reference driver's call sequence (/root/reference/USMain.py:12-24,92-224,257-289) through the
+stand-in packages, and the DAS beamformer ("next" row f1) against a numpy / scipy restatement."""
+import numpy as np
+import pytest
+
+from prt_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _das_numpy(ch, angles_deg, x, z, fs, c, pitch, t0, f_number):
+    n_a, n_e, T = ch.shape
+    xe = pitch * (np.arange(n_e) - (n_e - 1) / 2)
+    X, Z = np.meshgrid(x, z, indexing="ij")
+    out = np.zeros_like(X, dtype=np.float64)
+    for a in range(n_a):
+        th = np.deg2rad(angles_deg[a])
+        t_tx = (Z * np.cos(th) + X * np.sin(th)) / c
+        for e in range(n_e):
+            dx = X - xe[e]
+            t = t_tx + np.sqrt(dx * dx + Z * Z) / c - t0
+            s = t * fs
+            i0 = np.floor(s).astype(np.int64)
+            ok = (i0 >= 0) & (i0 + 1 < T)
+            if f_number > 0:
+                ok &= np.abs(dx) * 2 * f_number <= Z
+            i0c = np.clip(i0, 0, T - 2)
+            w = s - i0
+            v = ch[a, e, i0c] * (1 - w) + ch[a, e, i0c + 1] * w
+            out += np.where(ok, v, 0.0)
+    return out / n_a
+
+
+def test_das_matches_numpy():
+    from scipy.signal import hilbert
+    from prt_b200.engine import das_beamform, envelope
+    rng = np.random.default_rng(0)
+    n_a, n_e, T = 3, 16, 600
+    # smooth (band-limited) RF so that fp32 time-of-flight rounding cannot flip a whole sample
+    tt = np.arange(T) / 50e6
+    ch = np.stack([[np.sin(2 * np.pi * 3e6 * tt + 0.3 * e + a) * np.exp(-((tt - 6e-6 - 1e-7 * e) / 2e-6) ** 2)
+                    for e in range(n_e)] for a in range(n_a)]).astype(np.float32)
+    angles = np.array([-10.0, 0.0, 10.0])
+    x = np.linspace(-0.004, 0.004, 37)
+    z = np.linspace(0.002, 0.012, 101)
+    fs, c, pitch = 50e6, 1540.0, 3e-4
+    rf, env = das_beamform(ch, angles, x, z, fs, c, pitch, t0=0.0, f_number=0.0)
+    ref = _das_numpy(ch.astype(np.float64), angles, x, z, fs, c, pitch, 0.0, 0.0)
+    assert rf.shape == (37, 101)
+    assert np.abs(rf - ref).max() <= 2e-3 * np.abs(ref).max()       # fp32 time-of-flight * 50 MHz interpolation
+    # with an f-number the aperture edge may include / exclude one element where |dx| 2 f# == z to within an ulp
+    rf2, _ = das_beamform(ch, angles, x, z, fs, c, pitch, t0=0.0, f_number=0.83)
+    ref2 = _das_numpy(ch.astype(np.float64), angles, x, z, fs, c, pitch, 0.0, 0.83)
+    assert (np.abs(rf2 - ref2) <= 2e-3 * np.abs(ref2).max()).mean() > 0.995
+    ref_env = np.abs(hilbert(rf.astype(np.float64), axis=1))
+    assert np.abs(env - ref_env).max() <= 1e-4 * ref_env.max()
+    assert np.abs(envelope(rf) - env).max() <= 1e-6 * ref_env.max()
+
+
+def test_usmain_call_sequence():
+    """What USMain.py does, with 2 optimisation iterations instead of 25 and 64 samples per element so that the
+    finite-difference loss is not pure noise."""
+    from prt_b200 import shims
+    shims.install()
+    import drjit as dr
+    import mitsuba as mi
+    from ultraspy.beamformers.das import DelayAndSum
+    from ultraspy.probes.factory import build_probe
+    from ultraspy.scan import GridScan
+    mi.set_variant("llvm_ad_mono")
+    from CustomIntegrator import UltraIntegrator
+    from CustomSensor import UltraSensor
+    from CustomEmmitter import CustomEmitter
+    from CustomBSDF import UltraBSDF
+    mi.register_integrator("ultrasound_integrator", UltraIntegrator)
+    mi.register_sensor("ultrasound_sensor", UltraSensor)
+    mi.register_emitter('ultrasound_emitter', CustomEmitter)
+    mi.register_bsdf('ultrasound_bsdf', UltraBSDF)
+    d = scenes.usmain_scene_dict()
+    d["integrator"]["angles"] = dr.linspace(mi.Float, -15, 15, 5)
+    d["integrator"]["samples_per_element"] = 64
+    scene = mi.load_dict(d)
+    params = mi.traverse(scene)
+
+    def us_render(scene):
+        integrator = scene.integrator()
+        assert integrator.simulate_acquisition_parallel(scene) is True
+        channel_buf, delays = integrator.channel_buf, integrator.transmission_delays_buf
+        n_a, n_e, T = integrator.n_angles, integrator.n_elements, integrator.time_samples
+        assert channel_buf.shape == (n_a, n_e, T) and channel_buf.dtype == np.float32
+        assert np.isfinite(np.sum(channel_buf)) and np.max(channel_buf) > 0
+        assert np.allclose(integrator.angles.numpy(), [-15, -7.5, 0, 7.5, 15])
+        channel_data = channel_buf.reshape((n_a, n_e, T))
+        tx = delays.reshape((n_a, n_e))
+        probe = build_probe(geometry_type='linear', nb_elements=n_e, pitch=integrator.pitch, central_freq=integrator.frequency, bandwidth=70)
+        seq = {'emitted': np.tile(np.arange(n_e), (n_a, 1)), 'received': np.tile(np.arange(n_e), (n_a, 1))}
+        info = {'sampling_freq': integrator.fs, 't0': 0, 'prf': None, 'signal_duration': None, 'delays': tx,
+                'sound_speed': integrator.sound_speed, 'sequence_elements': seq}
+        bf = DelayAndSum(on_gpu=False)
+        bf.automatic_setup(info, probe)
+        assert str(bf)
+        lam = integrator.sound_speed / integrator.frequency
+        x_scan = np.arange(-0.04, 0.04 + lam / 4, lam / 4)
+        z_scan = np.arange(0.001, 0.05 + lam / 4, lam / 4)
+        scan = GridScan(x_scan, z_scan)
+        out = bf.beamform(channel_data[np.newaxis][0], scan)
+        env = bf.compute_envelope(out, scan).astype(np.float32)
+        assert env.shape == (len(x_scan), len(z_scan)) == (1040, 638)
+        db = 20 * np.log10(env + 1e-12)
+        mx = np.max(db)
+        img = (np.clip(db, mx - 60, mx) - (mx - 60)) / 60
+        return img.T
+
+    ref = us_render(scene)
+    assert ref.shape == (638, 1040) and 0.0 <= ref.min() and ref.max() == pytest.approx(1.0)
+    assert (ref > 0).mean() > 0.01
+
+    def forward(rough):
+        params['shape.bsdf.roughness'] = rough            # USMain.py:264
+        params.update()
+        return us_render(scene)
+
+    f0 = np.mean((forward(0.1) - ref) ** 2)
+    f1 = np.mean((forward(0.7) - ref) ** 2)
+    assert np.isfinite(f0) and np.isfinite(f1)
+    assert f1 < f0           # same seed, same roughness as the reference render (0.7) -> identical image
+    assert f1 == 0.0

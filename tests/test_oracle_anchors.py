@@ -218,3 +218,52 @@ def test_oracle_quirks(orc):
     pf = AcqParams.from_props(dm.integrator, dm.sensor, quirk_flags=orc.QF_CONNECT_TO_TARGET)
     b, _, s = orc.OracleScene(dm).acquire(pf, seed=1, spp=4, prec=32)
     assert s["deposits"] > 0
+
+
+@pytest.mark.parametrize("name,order", [("Plate_Box", "intended"), ("Sphere_Box", "intended"), ("Plane_Floating", "mitsuba")])
+def test_c_oracle_equals_python_transliteration(orc, name, order):
+    """oracle/orc.c (C, f64) vs oracle/pyref.py (pure Python, f64, written independently from the reference's
+    _trace_single_ray): same injected PCG32 streams -> the same buffer, bin for bin."""
+    import pyref
+    desc = scenes.ultrasound_scene(name, order)
+    p = AcqParams.from_props(desc.integrator, desc.sensor)
+    buf_c, tx_c, st_c = orc.OracleScene(desc).acquire(p, seed=4, spp=2, prec=64, n_threads=2)
+    buf_p, tx_p, st_p = pyref.acquire(pyref.shapes_from_desc(desc), p, seed=4, spp=2)
+    assert st_c["paths"] == st_p["paths"] == 640
+    assert st_c["segments"] == st_p["segments"] and st_c["rays"] == st_p["rays"] and st_c["deposits"] == st_p["deposits"]
+    assert np.allclose(tx_c, tx_p, rtol=1e-13, atol=0)
+    assert np.array_equal(buf_c != 0, buf_p != 0)
+    assert np.allclose(buf_c, buf_p, rtol=1e-6, atol=1e-15)
+
+
+def test_pinned_pool_never_hands_out_a_live_buffer():
+    """engine.Context.pinned_array: a result the caller still references (directly or through a derived view) is
+    never reused (host logic; allocator faked, no GPU)."""
+    import ctypes as C
+    from prt_b200 import engine
+
+    class FakeL:
+        def __init__(self):
+            self.keep = []
+
+        def prt_host_alloc(self, h, n, out):
+            b = (C.c_byte * n)()
+            self.keep.append(b)
+            out._obj.value = C.addressof(b)
+            return 0
+
+    ctx = object.__new__(engine.Context)
+    ctx.L, ctx.h = FakeL(), None
+    a = ctx.pinned_array((2, 2), np.float32)
+    b = ctx.pinned_array((2, 2), np.float32)
+    assert a.ctypes.data != b.ctypes.data
+    pa = a.ctypes.data
+    del a
+    c = ctx.pinned_array((2, 2), np.float32)
+    assert c.ctypes.data == pa                       # released -> reused
+    r = c.reshape(4)[1:]
+    del c
+    d = ctx.pinned_array((2, 2), np.float32)
+    assert d.ctypes.data != pa                       # a derived view keeps it busy
+    del r
+    assert ctx.pinned_array((2, 2), np.float32).ctypes.data == pa
