@@ -527,4 +527,45 @@ __device__ __forceinline__ void ultra_bsdf_sample(float3 wi, float3 ng, float3 n
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// light-transport helpers shared by the megakernel (prt_path.cu) and the wavefront kernels (prt_wavefront.cu):
+// Mitsuba's mis_weight, warp::square_to_uniform_disk_concentric and fresnel()
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mis_weight(float a, float b) {
+    a *= a;
+    b *= b;
+    float w = a / (a + b);
+    return isfinite(w) ? w : 0.0f;
+}
+
+__device__ __forceinline__ void disk_concentric(float ux, float uy, float &ox, float &oy) {
+    float x = fmaf(2.0f, ux, -1.0f), y = fmaf(2.0f, uy, -1.0f);
+    if (x == 0.0f && y == 0.0f) { ox = 0.0f; oy = 0.0f; return; }
+    bool q = fabsf(x) < fabsf(y);
+    float r = q ? y : x, rp = q ? x : y;
+    float phi = 0.25f * PRT_PI_F * rp / r;
+    if (q) phi = 0.5f * PRT_PI_F - phi;
+    float s, c;
+    sincosf(phi, &s, &c);
+    ox = r * c;
+    oy = r * s;
+}
+
+// mitsuba fresnel(cos_theta_i, eta)
+__device__ __forceinline__ float fresnel_dielectric(float cos_i, float eta, float &cos_t, float &eta_it, float &eta_ti) {
+    bool outside = cos_i >= 0.0f;
+    float rcp_eta = 1.0f / eta;
+    eta_it = outside ? eta : rcp_eta;
+    eta_ti = outside ? rcp_eta : eta;
+    float ct2 = 1.0f - (1.0f - cos_i * cos_i) * eta_ti * eta_ti;
+    float ci = fabsf(cos_i), ct = sqrtf(fmaxf(ct2, 0.0f));
+    float a_s = (-eta_it * ct + ci) / (eta_it * ct + ci);
+    float a_p = (-eta_it * ci + ct) / (eta_it * ci + ct);
+    float r = 0.5f * (a_s * a_s + a_p * a_p);
+    if (eta == 1.0f) r = 0.0f;
+    else if (ci == 0.0f) r = 1.0f;
+    cos_t = cos_i >= 0.0f ? -ct : ct;
+    return r;
+}
+
 }  // namespace prt

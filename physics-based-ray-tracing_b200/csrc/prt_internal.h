@@ -52,6 +52,8 @@ struct prt_context {
     uint64_t *stats_dev;                      // 8 x u64
     double   *angles_dev; size_t angles_cap;
     void     *pinned;    size_t pinned_cap;   // pinned staging for D2H of results
+    void     *wf_dev = nullptr; size_t wf_cap = 0;   // wavefront path-tracer state / queues (prt_wavefront.cu)
+    int       last_launches = 0;              // kernels enqueued by the most recent render call
 };
 
 struct prt_scene {

@@ -147,6 +147,7 @@ int prt_destroy(prt_context *c) {
     if (c->angles_dev) cudaFree(c->angles_dev);
     if (c->stats_dev) cudaFree(c->stats_dev);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->wf_dev) cudaFree(c->wf_dev);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->slice_done[0]);

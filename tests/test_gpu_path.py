@@ -112,3 +112,37 @@ def test_heightfield_lbvh_against_oracle(orc):
     assert fst["paths"] == rst["paths"] and abs(fst["segments"] - rst["segments"]) <= 2e-3 * rst["segments"]
     gi, ci = _image(film), _image(ref)
     assert _rel_mse(gi, ci) < 1e-3
+
+
+def _render_mode(dev, rp, mode, monkeypatch, batch=None, **kw):
+    monkeypatch.setenv("PRT_PT_MODE", mode)
+    if batch is None:
+        monkeypatch.delenv("PRT_WF_BATCH", raising=False)
+    else:
+        monkeypatch.setenv("PRT_WF_BATCH", str(batch))
+    return dev.render_path(rp, **kw)
+
+
+@pytest.mark.parametrize("which", ["cbox", "heightfield"])
+def test_wavefront_equals_megakernel(which, monkeypatch):
+    """The wavefront pipeline (queues, dynamic ray fetch, per-material shading kernels) and the tile megakernel run
+    the same shading code on the same PCG32 streams: identical path/segment/ray counts, and films equal up to the
+    order of the float adds inside a tile."""
+    desc = scenes.cbox_scene(80, 16) if which == "cbox" else scenes.heightfield_scene(120, (96, 54), 4)
+    scene = mi.Scene(desc)
+    dev = scene.device()
+    rp = scene.integrator().render_params(scene)
+    spp = 16 if which == "cbox" else 4
+    a, sa = _render_mode(dev, rp, "mega", monkeypatch, seed=9, spp=spp)
+    b, sb = _render_mode(dev, rp, "wavefront", monkeypatch, seed=9, spp=spp)
+    for k in ("paths", "segments", "rays", "shadow_rays"):
+        assert sa[k] == sb[k], k
+    assert sb["launches"] > 4
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+    # several batches (forced small) and sample shards give the same film again
+    c, sc_ = _render_mode(dev, rp, "wavefront", monkeypatch, batch=1, seed=9, spp=spp)
+    assert sc_["rays"] == sa["rays"] and sc_["launches"] > sb["launches"]
+    assert np.allclose(a, c, rtol=1e-5, atol=1e-6)
+    parts = [_render_mode(dev, rp, "wavefront", monkeypatch, seed=9, spp=spp, sample_offset=g, sample_stride=2) for g in range(2)]
+    assert sum(s["rays"] for _, s in parts) == sa["rays"]
+    assert np.allclose(sum(f.astype(np.float64) for f, _ in parts), a, rtol=2e-5, atol=1e-6)
