@@ -80,6 +80,10 @@ typedef struct {
     float    sah_cost;          /* SAH cost of the final tree (root area normalised)   */
     float    scene_lo[3], scene_hi[3];
     uint64_t device_bytes;      /* bytes of device memory held by the scene            */
+    uint32_t n_nodes8;          /* nodes of the compressed 8-wide BVH (80 B each), 0 = none */
+    uint32_t bvh8_levels;
+    float    bvh8_build_ms;     /* collapse + quantisation + triangle reorder, CUDA-event timed */
+    float    _pad;
 } prt_bvh_stats;
 /* SoA upload + GPU LBVH build (Morton codes -> radix sort -> Karras hierarchy -> bottom-up refit) */
 int prt_scene_commit(prt_scene *, prt_bvh_stats *out /* nullable */);

@@ -369,8 +369,9 @@ __global__ void k_sah(int n, const float *__restrict__ nodes, const int2 *__rest
 }
 
 int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri_v_out, uint32_t *order_out,
-               float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t st) {
+               float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t st, Bvh8Out *bvh8) {
     (void) ctx;
+    if (bvh8) *bvh8 = Bvh8Out{ nullptr, nullptr, nullptr, 0, 0, 0.0f };
     if (n == 0) {
         *root_ref = -1;
         return PRT_OK;
@@ -427,6 +428,20 @@ int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri
     PRT_CUDA(cudaEventRecord(e1, st));
     PRT_CUDA(cudaStreamSynchronize(st));
     PRT_CUDA(cudaGetLastError());
+    if (bvh8 && n >= 2) {
+        cudaEvent_t b0, b1;
+        PRT_CUDA(cudaEventCreate(&b0));
+        PRT_CUDA(cudaEventCreate(&b1));
+        PRT_CUDA(cudaEventRecord(b0, st));
+        int rc = build_bvh8(n, tri_v_out, (const float *) nodes_out, children, ranges, &bvh8->nodes8, &bvh8->n_nodes8, &bvh8->tri_v8,
+                            &bvh8->tri8_sorted, &bvh8->levels, st);
+        if (rc) return rc;
+        PRT_CUDA(cudaEventRecord(b1, st));
+        PRT_CUDA(cudaStreamSynchronize(st));
+        PRT_CUDA(cudaEventElapsedTime(&bvh8->build_ms, b0, b1));
+        cudaEventDestroy(b0);
+        cudaEventDestroy(b1);
+    }
     *root_ref = (n <= (uint32_t) MAX_LEAF) ? ~(int) ((0u << 2) | (n - 1)) : 0;
     if (stats) {
         float ms = 0.0f, hb[8];

@@ -52,6 +52,11 @@ struct DScene {
     const float     *em_inv_area;    // [n_emitters]
     const int       *shape_emitter;  // [n_shapes] emitter index or -1
     int n_emitters, n_shapes;
+    // compressed 8-wide BVH over the same triangles (prt_bvh8.cuh); n_nodes8 == 0: not built
+    const float4    *nodes8;         // [n_nodes8][5]
+    const float4    *tri_v8;         // [n_tris][3] vertices in BVH8 leaf order
+    const uint32_t  *tri8_sorted;    // [n_tris] BVH8 triangle position -> sorted (LBVH) position
+    int n_nodes8;
 };
 
 // ------------------------------------------------------------------------------------------------

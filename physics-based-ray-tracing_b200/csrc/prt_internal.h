@@ -67,6 +67,11 @@ struct prt_scene {
     prt::DPrim     *prims_dev;
     prt::DMaterial *mats_dev;
     float4 *nodes_dev, *tri_v_dev, *tri_n_dev;
+    float4 *nodes8_dev = nullptr, *tri_v8_dev = nullptr;   // compressed 8-wide BVH (prt_bvh8.cu)
+    uint32_t *tri8_sorted_dev = nullptr;
+    uint32_t n_nodes8 = 0;
+    int bvh8_levels = 0;
+    float bvh8_build_ms = 0.0f;
     int4   *tri_info_dev;
     float4 *em_tri_dev;
     int    *em_first_dev, *shape_emitter_dev;
@@ -83,7 +88,19 @@ namespace prt {
 // prt_bvh.cu: builds the LBVH over `n` triangles given in INPUT order.
 //   tri_v_in  [n][3] float4 world-space vertices (device), reordered into tri_v_out in sorted order
 //   order_out [n] sorted position -> input index
+struct Bvh8Out {
+    float4 *nodes8;
+    float4 *tri_v8;
+    uint32_t *tri8_sorted;
+    uint32_t n_nodes8;
+    int levels;
+    float build_ms;
+};
+// bvh8 != nullptr: also derive the compressed 8-wide BVH from the binary tree (buffers owned by the caller afterwards)
 int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri_v_out, uint32_t *order_out,
-               float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t stream);
+               float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t stream, Bvh8Out *bvh8 = nullptr);
+int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, const int2 *children, const int2 *ranges,
+               float4 **out_nodes8, uint32_t *out_n_nodes8, float4 **out_tri_v8, uint32_t **out_tri8_sorted, int *out_levels,
+               cudaStream_t st);
 int ensure_scratch(prt_context *ctx, size_t acc_floats, size_t aux_floats, size_t n_angles);
 }  // namespace prt

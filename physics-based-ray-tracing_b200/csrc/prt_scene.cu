@@ -94,6 +94,10 @@ prt::DScene prt_scene::view() const {
     v.shape_emitter = shape_emitter_dev;
     v.n_emitters = n_emitters;
     v.n_shapes = n_shapes;
+    v.nodes8 = nodes8_dev;
+    v.tri_v8 = tri_v8_dev;
+    v.tri8_sorted = tri8_sorted_dev;
+    v.n_nodes8 = (int) n_nodes8;
     return v;
 }
 
@@ -209,6 +213,12 @@ static void free_device(prt_scene *s) {
     if (s->tri_v_dev) cudaFree(s->tri_v_dev);
     if (s->tri_n_dev) cudaFree(s->tri_n_dev);
     if (s->tri_info_dev) cudaFree(s->tri_info_dev);
+    if (s->nodes8_dev) cudaFree(s->nodes8_dev);
+    if (s->tri_v8_dev) cudaFree(s->tri_v8_dev);
+    if (s->tri8_sorted_dev) cudaFree(s->tri8_sorted_dev);
+    s->nodes8_dev = s->tri_v8_dev = nullptr;
+    s->tri8_sorted_dev = nullptr;
+    s->n_nodes8 = 0;
     if (s->em_tri_dev) cudaFree(s->em_tri_dev);
     if (s->em_first_dev) cudaFree(s->em_first_dev);
     if (s->shape_emitter_dev) cudaFree(s->shape_emitter_dev);
@@ -409,8 +419,16 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
         PRT_CUDA(cudaMalloc(&s->tri_info_dev, sizeof(int4) * nt));
         PRT_CUDA(cudaMalloc(&s->nodes_dev, sizeof(float4) * 4 * (nt > 1 ? nt - 1 : 1)));
         bytes += sizeof(float4) * 3 * nt + sizeof(int4) * nt + sizeof(float4) * 4 * (nt > 1 ? nt - 1 : 1);
-        int rc = build_lbvh(s->ctx, v_in, (uint32_t) nt, s->tri_v_dev, order, s->nodes_dev, &s->root_ref, &s->stats, st);
+        Bvh8Out b8;
+        int rc = build_lbvh(s->ctx, v_in, (uint32_t) nt, s->tri_v_dev, order, s->nodes_dev, &s->root_ref, &s->stats, st, &b8);
         if (rc) return rc;
+        s->nodes8_dev = b8.nodes8;
+        s->tri_v8_dev = b8.tri_v8;
+        s->tri8_sorted_dev = b8.tri8_sorted;
+        s->n_nodes8 = b8.n_nodes8;
+        s->bvh8_levels = b8.levels;
+        s->bvh8_build_ms = b8.build_ms;
+        if (b8.n_nodes8) bytes += sizeof(float4) * 5 * (size_t) b8.n_nodes8 + (sizeof(float4) * 3 + sizeof(uint32_t)) * nt;
         k_gather_aux<<<(unsigned) ((nt + 255) / 256), 256, 0, st>>>(order, (uint32_t) nt, i_in, n_in, s->tri_info_dev, s->tri_n_dev);
         PRT_CUDA(cudaStreamSynchronize(st));
         PRT_CUDA(cudaGetLastError());
@@ -461,6 +479,10 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
     s->stats.n_primitives = (uint32_t) s->prims.size();
     s->stats.n_triangles = s->n_tris;
     s->stats.device_bytes = bytes;
+    s->stats.n_nodes8 = s->n_nodes8;
+    s->stats.bvh8_levels = (uint32_t) s->bvh8_levels;
+    s->stats.bvh8_build_ms = s->bvh8_build_ms;
+    s->stats._pad = 0.0f;
     s->committed = true;
     if (out) *out = s->stats;
     return PRT_OK;

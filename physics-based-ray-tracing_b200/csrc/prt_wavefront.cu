@@ -24,6 +24,7 @@
 // bounce, zeroed once), so the host never synchronises inside a batch.
 #include <cstdlib>
 
+#include "prt_bvh8.cuh"
 #include "prt_internal.h"
 #include "prt_path.h"
 
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_generate(const PtDev P,
 // ------------------------------------------------------------------------------------------------------------------
 // ray queries with dynamic fetch
 // ------------------------------------------------------------------------------------------------------------------
-template <bool ANY>
+template <bool ANY, bool W8>
 __global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(const PtDev P, const WfBuf B, const int bounce) {
     __shared__ DPrim sprims[MAX_SMEM_PRIMS];
     const DScene &sc = P.sc;
@@ -156,17 +157,25 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(const PtDev P, co
     bool dry = false;                    // warp-uniform: the queue is exhausted
     bool has = false;
     uint32_t slot = 0;                   // path slot (closest) / shadow-queue position (any)
-    float3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0);
+    float3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
     RayPre rp = ray_precompute(d);
     float tbest = 0.0f, b1 = 0.0f, b2 = 0.0f, prim_t = 0.0f;
-    int best = -1, best_prim = -1, sp = 0, ref = DONE;
-    int   stack_ref[PRT_STACK];
-    float stack_t[PRT_STACK];
+    int best = -1, best_prim = -1, sp = 0;
+    // BVH2 state (W8 == false)
+    float3 inv = mk3(0, 0, 0);
+    int ref = DONE;
+    int   stack_ref[W8 ? 1 : PRT_STACK];
+    float stack_t[W8 ? 1 : PRT_STACK];
+    // BVH8 state (W8 == true): current node group (child base, hit bits | imask), its triangle group, stack of groups
+    Bvh8Ray r8 = bvh8_ray(o, d);
+    uint2 ng = make_uint2(0, 0);
+    uint2 gstack[W8 ? BVH8_STACK : 1];
+    bool busy = false;
     unsigned n_rays = 0, n_valid = 0;
 
     for (;;) {
         // ---- retire finished rays ----
-        const bool fin = has && ref == DONE;
+        const bool fin = has && (W8 ? !busy : ref == DONE);
         if (__any_sync(FULL, fin)) {
             if (!ANY) {
                 int qi = -1;
@@ -174,8 +183,9 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(const PtDev P, co
                     int id = -1, material = 0;
                     float t = tbest;
                     if (best >= 0 && (best_prim < 0 || tbest < prim_t)) {
-                        id = sc.n_prims + best;
-                        material = __ldg(&sc.tri_info[best].z);
+                        const int sorted = W8 ? (int) __ldg(sc.tri8_sorted + best) : best;
+                        id = sc.n_prims + sorted;
+                        material = __ldg(&sc.tri_info[sorted].z);
                     } else if (best_prim >= 0) {
                         id = best_prim;
                         t = prim_t;
@@ -255,9 +265,16 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(const PtDev P, co
                     }
                     if (!ANY) tbest = prim_t;
                     rp = ray_precompute(d);
-                    inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
                     sp = 0;
-                    ref = (sc.n_tris == 0 || blocked) ? DONE : sc.root_ref;
+                    const bool go = !(sc.n_tris == 0 || blocked);
+                    if (W8) {
+                        r8 = bvh8_ray(o, d);
+                        ng = make_uint2(0u, 0x80000000u);
+                        busy = go;
+                    } else {
+                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        ref = go ? sc.root_ref : DONE;
+                    }
                     if (ANY && blocked) best = 0;
                 }
                 pool_next += min(avail, __popc(need));
@@ -266,6 +283,39 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(const PtDev P, co
         }
         if (!__any_sync(FULL, has)) break;
 
+        if (W8) {
+            // ---- one wide node per lane and iteration, then the triangles it yielded ----
+            if (busy) {
+                uint2 tg = make_uint2(0u, 0u);
+                if (ng.y > 0x00ffffffu) {
+                    const uint32_t hits = ng.y, imask8 = ng.y & 0xffu;
+                    const int bit = 31 - __clz(hits);
+                    ng.y &= ~(1u << bit);
+                    if (ng.y > 0x00ffffffu && sp < BVH8_STACK) gstack[sp++] = ng;
+                    const uint32_t slot_index = (uint32_t) (bit - 24) ^ (r8.octinv4 & 0xffu);
+                    const uint32_t rel = __popc(imask8 & ~(0xffffffffu << slot_index));
+                    uint32_t child_base, tri_base, imask;
+                    const uint32_t hm = bvh8_node(sc.nodes8, ng.x + rel, r8, tbest, child_base, tri_base, imask);
+                    ng = make_uint2(child_base, (hm & 0xff000000u) | imask);
+                    tg = make_uint2(tri_base, hm & 0x00ffffffu);
+                }
+                while (tg.y) {
+                    const int bit = 31 - __clz(tg.y);
+                    tg.y &= ~(1u << bit);
+                    const uint32_t ti = tg.x + (uint32_t) bit;
+                    const float4 *tv = sc.tri_v8 + 3 * (size_t) ti;
+                    const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
+                    if (intersect_tri_wt(rp, o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+                        best = (int) ti;
+                        if (ANY) { busy = false; break; }
+                    }
+                }
+                if (busy && ng.y <= 0x00ffffffu) {
+                    if (sp > 0) ng = gstack[--sp];
+                    else busy = false;
+                }
+            }
+        } else {
 #define PRT_POP()                                                        \
     do {                                                                 \
         ref = DONE;                                                      \
@@ -274,45 +324,46 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(const PtDev P, co
             if (stack_t[sp] <= tbest) { ref = stack_ref[sp]; break; }    \
         }                                                                \
     } while (0)
-        // ---- inner nodes: every lane descends until it holds a leaf or is done ----
-        while ((unsigned) ref < (unsigned) DONE) {
-            const float4 *nd = sc.nodes + 4 * (size_t) ref;
-            const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
-            const float tl = box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tbest);
-            const float tr = box_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, inv, tbest);
-            const int rl = __float_as_int(q3.x), rr = __float_as_int(q3.y);
-            const bool hl = tl < PRT_INF, hr = tr < PRT_INF;
-            if (hl && hr) {
-                const bool lf = tl <= tr;
-                if (sp < PRT_STACK) {
-                    stack_ref[sp] = lf ? rr : rl;
-                    stack_t[sp] = lf ? tr : tl;
-                    sp++;
-                }
-                ref = lf ? rl : rr;
-            } else if (hl || hr) {
-                ref = hl ? rl : rr;
-            } else {
-                PRT_POP();
-            }
-        }
-        // ---- leaf ----
-        if (ref < 0) {
-            const int code = ~ref;
-            const int first = code >> 2, count = (code & 3) + 1;
-            bool stop = false;
-            for (int j = 0; j < count; j++) {
-                const float4 *tv = sc.tri_v + 3 * (size_t) (first + j);
-                const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
-                if (intersect_tri_wt(rp, o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
-                    best = first + j;
-                    if (ANY) { stop = true; break; }
+            // ---- inner nodes: every lane descends until it holds a leaf or is done ----
+            while ((unsigned) ref < (unsigned) DONE) {
+                const float4 *nd = sc.nodes + 4 * (size_t) ref;
+                const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+                const float tl = box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tbest);
+                const float tr = box_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, inv, tbest);
+                const int rl = __float_as_int(q3.x), rr = __float_as_int(q3.y);
+                const bool hl = tl < PRT_INF, hr = tr < PRT_INF;
+                if (hl && hr) {
+                    const bool lf = tl <= tr;
+                    if (sp < PRT_STACK) {
+                        stack_ref[sp] = lf ? rr : rl;
+                        stack_t[sp] = lf ? tr : tl;
+                        sp++;
+                    }
+                    ref = lf ? rl : rr;
+                } else if (hl || hr) {
+                    ref = hl ? rl : rr;
+                } else {
+                    PRT_POP();
                 }
             }
-            if (stop) ref = DONE;
-            else PRT_POP();
-        }
+            // ---- leaf ----
+            if (ref < 0) {
+                const int code = ~ref;
+                const int first = code >> 2, count = (code & 3) + 1;
+                bool stop = false;
+                for (int j = 0; j < count; j++) {
+                    const float4 *tv = sc.tri_v + 3 * (size_t) (first + j);
+                    const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
+                    if (intersect_tri_wt(rp, o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+                        best = first + j;
+                        if (ANY) { stop = true; break; }
+                    }
+                }
+                if (stop) ref = DONE;
+                else PRT_POP();
+            }
 #undef PRT_POP
+        }
     }
     wf_add_stat(P, 2, n_rays);
     if (ANY) wf_add_stat(P, 3, n_rays);
@@ -436,8 +487,13 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
     int g_gen = 1, g_ext = 1, g_sh = 1, g_shade[WF_QUEUES] = { 1, 1, 1 };
     int rc;
     if ((rc = wf_grid(c, (const void *) k_wf_generate, WF_SHADE_THREADS, &g_gen))) return rc;
-    if ((rc = wf_grid(c, (const void *) k_wf_trace<false>, WF_TRACE_THREADS, &g_ext))) return rc;
-    if ((rc = wf_grid(c, (const void *) k_wf_trace<true>, WF_TRACE_THREADS, &g_sh))) return rc;
+    // BVH8c by default when it exists; PRT_BVH=2 keeps the binary tree (A/B runs, parity tests between the two)
+    const char *bsel = getenv("PRT_BVH");
+    const bool w8 = P.sc.n_nodes8 > 0 && !(bsel && bsel[0] == '2');
+    const void *k_ext = w8 ? (const void *) k_wf_trace<false, true> : (const void *) k_wf_trace<false, false>;
+    const void *k_sh = w8 ? (const void *) k_wf_trace<true, true> : (const void *) k_wf_trace<true, false>;
+    if ((rc = wf_grid(c, k_ext, WF_TRACE_THREADS, &g_ext))) return rc;
+    if ((rc = wf_grid(c, k_sh, WF_TRACE_THREADS, &g_sh))) return rc;
     if ((rc = wf_grid(c, (const void *) k_wf_shade<0>, WF_SHADE_THREADS, &g_shade[0]))) return rc;
     if ((rc = wf_grid(c, (const void *) k_wf_shade<1>, WF_SHADE_THREADS, &g_shade[1]))) return rc;
     if ((rc = wf_grid(c, (const void *) k_wf_shade<2>, WF_SHADE_THREADS, &g_shade[2]))) return rc;
@@ -449,7 +505,8 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
         k_wf_generate<<<g_gen, WF_SHADE_THREADS, 0, st>>>(P, B);
         launches++;
         for (int b = 0; b < bounces; b++) {
-            k_wf_trace<false><<<g_ext, WF_TRACE_THREADS, 0, st>>>(P, B, b);
+            if (w8) k_wf_trace<false, true><<<g_ext, WF_TRACE_THREADS, 0, st>>>(P, B, b);
+            else k_wf_trace<false, false><<<g_ext, WF_TRACE_THREADS, 0, st>>>(P, B, b);
             launches++;
             if (P.kind_mask & (1u << PRT_MAT_DIFFUSE)) { k_wf_shade<0><<<g_shade[0], WF_SHADE_THREADS, 0, st>>>(P, B, b); launches++; }
             if (P.kind_mask & (1u << PRT_MAT_DIELECTRIC)) { k_wf_shade<1><<<g_shade[1], WF_SHADE_THREADS, 0, st>>>(P, B, b); launches++; }
@@ -458,7 +515,8 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
                 launches++;
             }
             if (b + 1 < P.max_depth && (P.kind_mask & (1u << PRT_MAT_DIFFUSE)) && P.sc.n_emitters > 0) {
-                k_wf_trace<true><<<g_sh, WF_TRACE_THREADS, 0, st>>>(P, B, b);
+                if (w8) k_wf_trace<true, true><<<g_sh, WF_TRACE_THREADS, 0, st>>>(P, B, b);
+                else k_wf_trace<true, false><<<g_sh, WF_TRACE_THREADS, 0, st>>>(P, B, b);
                 launches++;
             }
         }
