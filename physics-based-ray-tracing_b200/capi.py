@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprt_b200.so")
+LIB_PATH = os.environ.get("PRT_B200_LIB") or os.path.join(_HERE, "libprt_b200.so")   # override: A/B runs of kernel builds
 
 PRIM_KINDS = {"sphere": 0, "rectangle": 1, "cone": 2, "disk": 3, "cylinder": 4}
 MAT_KINDS = {"ultra": 0, "diffuse": 1, "dielectric": 2, "conductor": 3, "null": 4}

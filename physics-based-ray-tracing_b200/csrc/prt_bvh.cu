@@ -428,7 +428,7 @@ int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri
     PRT_CUDA(cudaEventRecord(e1, st));
     PRT_CUDA(cudaStreamSynchronize(st));
     PRT_CUDA(cudaGetLastError());
-    if (bvh8 && n >= 2) {
+    if (bvh8) {
         cudaEvent_t b0, b1;
         PRT_CUDA(cudaEventCreate(&b0));
         PRT_CUDA(cudaEventCreate(&b1));

@@ -8,6 +8,7 @@
 // triangles of its leaf children with two atomics, and writes the binary roots of its inner children as the tasks of
 // the next level.  The host reads one counter per level (~log8 N levels).
 #include <cfloat>
+#include <cstring>
 
 #include "prt_bvh8.cuh"
 #include "prt_internal.h"
@@ -166,7 +167,26 @@ __global__ void __launch_bounds__(128) k_bvh8_level(int begin, int end, int *__r
     out[4] = make_float4(__uint_as_float(pack4(q[4])), __uint_as_float(pack4(q[4] + 4)), __uint_as_float(pack4(q[5])), __uint_as_float(pack4(q[5] + 4)));
 }
 
-// n >= 2 triangles.  nodes2 (16 floats / binary node, padded child boxes), children, ranges: the LBVH's arrays.
+// After the per-triangle tables exist (sorted order): stamp every BVH8 triangle with what a hit needs, so that retiring a
+// ray costs no dependent loads: v1.w = bits((sorted index << 2) | shading queue of its material)
+__global__ void k_bvh8_annotate(uint32_t n, const uint32_t *__restrict__ tri8_sorted, const int4 *__restrict__ tri_info,
+                                const DMaterial *__restrict__ mats, float4 *__restrict__ tri_v8) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t sorted = tri8_sorted[i];
+    const int kind = mats[tri_info[sorted].z].kind;
+    const uint32_t qi = kind == PRT_MAT_DIFFUSE ? 0u : (kind == PRT_MAT_DIELECTRIC ? 1u : 2u);
+    tri_v8[3 * (size_t) i + 1].w = __uint_as_float((sorted << 2) | qi);
+}
+
+int bvh8_annotate(uint32_t n, const uint32_t *tri8_sorted, const int4 *tri_info, const DMaterial *mats, float4 *tri_v8, cudaStream_t st) {
+    if (!n || !tri_v8) return PRT_OK;
+    k_bvh8_annotate<<<(n + 255) / 256, 256, 0, st>>>(n, tri8_sorted, tri_info, mats, tri_v8);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_OK;
+}
+
+// n >= 1 triangles.  nodes2 (16 floats / binary node, padded child boxes), children, ranges: the LBVH's arrays.
 // On success *out_nodes8 / *out_tri_v8 / *out_tri8_sorted are fresh device allocations owned by the caller.
 int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, const int2 *children, const int2 *ranges,
                float4 **out_nodes8, uint32_t *out_n_nodes8, float4 **out_tri_v8, uint32_t **out_tri8_sorted, int *out_levels,
@@ -175,7 +195,48 @@ int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, cons
     *out_tri_v8 = nullptr;
     *out_tri8_sorted = nullptr;
     *out_n_nodes8 = 0;
-    if (n < 2) return PRT_OK;
+    *out_levels = 0;
+    if (n == 0) return PRT_OK;
+    if (n == 1) {
+        // no binary tree exists: one wide node whose slot 0 is a one-triangle leaf covering the node's whole grid
+        float4 v[3];
+        PRT_CUDA(cudaMemcpyAsync(v, tri_v_sorted, sizeof v, cudaMemcpyDeviceToHost, st));
+        PRT_CUDA(cudaStreamSynchronize(st));
+        float lo[3] = { fminf(v[0].x, fminf(v[1].x, v[2].x)), fminf(v[0].y, fminf(v[1].y, v[2].y)), fminf(v[0].z, fminf(v[1].z, v[2].z)) };
+        float hi[3] = { fmaxf(v[0].x, fmaxf(v[1].x, v[2].x)), fmaxf(v[0].y, fmaxf(v[1].y, v[2].y)), fmaxf(v[0].z, fmaxf(v[1].z, v[2].z)) };
+        uint32_t eb[3];
+        for (int a = 0; a < 3; a++) {
+            const float pad = 4.0f * 1.1920929e-7f * fmaxf(fmaxf(fabsf(lo[a]), fabsf(hi[a])), hi[a] - lo[a]) + 1e-30f;
+            lo[a] -= pad;
+            hi[a] += pad;
+            int e;
+            frexpf(fmaxf(hi[a] - lo[a], 1e-30f) / 254.0f, &e);
+            e = e < -125 ? -125 : (e > 126 ? 126 : e);
+            eb[a] = (uint32_t) (e + 127);
+        }
+        auto bits = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+        float4 node[5];
+        node[0] = make_float4(lo[0], lo[1], lo[2], bits(eb[0] | (eb[1] << 8) | (eb[2] << 16)));
+        node[1] = make_float4(bits(0u), bits(0u), bits(1u << 5), bits(0u));
+        const uint32_t qlo = 0xffffff00u, qhi = 0x000000ffu;     // slot 0: [0, 255]; empty slots: lo 255 > hi 0
+        node[2] = make_float4(bits(qlo), bits(0xffffffffu), bits(qlo), bits(0xffffffffu));
+        node[3] = make_float4(bits(qlo), bits(0xffffffffu), bits(qhi), bits(0u));
+        node[4] = make_float4(bits(qhi), bits(0u), bits(qhi), bits(0u));
+        float4 *nodes8 = nullptr, *tv8 = nullptr;
+        uint32_t *map = nullptr;
+        PRT_CUDA(cudaMalloc(&nodes8, sizeof node));
+        PRT_CUDA(cudaMalloc(&tv8, sizeof v));
+        PRT_CUDA(cudaMalloc(&map, sizeof(uint32_t)));
+        PRT_CUDA(cudaMemcpy(nodes8, node, sizeof node, cudaMemcpyHostToDevice));
+        PRT_CUDA(cudaMemcpy(tv8, v, sizeof v, cudaMemcpyHostToDevice));
+        PRT_CUDA(cudaMemset(map, 0, sizeof(uint32_t)));
+        *out_nodes8 = nodes8;
+        *out_n_nodes8 = 1;
+        *out_tri_v8 = tv8;
+        *out_tri8_sorted = map;
+        *out_levels = 1;
+        return PRT_OK;
+    }
     const size_t cap = (size_t) n;                 // every wide node opens a distinct binary node with > 3 triangles
     float4 *tmp_nodes = nullptr, *tri_v8 = nullptr;
     uint32_t *tri8_sorted = nullptr;

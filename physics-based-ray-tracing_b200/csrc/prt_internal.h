@@ -99,6 +99,7 @@ struct Bvh8Out {
 // bvh8 != nullptr: also derive the compressed 8-wide BVH from the binary tree (buffers owned by the caller afterwards)
 int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri_v_out, uint32_t *order_out,
                float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t stream, Bvh8Out *bvh8 = nullptr);
+int bvh8_annotate(uint32_t n, const uint32_t *tri8_sorted, const int4 *tri_info, const DMaterial *mats, float4 *tri_v8, cudaStream_t st);
 int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, const int2 *children, const int2 *ranges,
                float4 **out_nodes8, uint32_t *out_n_nodes8, float4 **out_tri_v8, uint32_t **out_tri8_sorted, int *out_levels,
                cudaStream_t st);

@@ -6,16 +6,20 @@
 // the same per-path PCG32 streams (the Mitsuba `path` integrator of /root/reference/scenes/cbox.xml:5-9, restated
 // from SURVEY.md Appendix C.7) -- but moves the two ray queries into their own persistent kernels:
 //
-//   k_wf_generate            camera rays of a batch of samples -> path state (SoA, float4 per field) + extend queue
+//   k_wf_generate            camera rays of a batch of samples -> path state (SoA, float4 per field) + ray records
 //   per bounce b:
-//     k_wf_trace<false>      closest hit.  Persistent warps pull rays from the queue in chunks; a lane whose ray is
-//                            finished retires it and takes the next one, so the heavy-tailed traversal length of an
-//                            incoherent ray (profiles/r01_summary.md: 176 node steps in a warp whose rays need 28 on
-//                            average) no longer idles the other 31 lanes.  Retiring classifies the hit by material
-//                            and appends the path to that material's shading queue (warp ballot + one atomic).
+//     k_wf_trace<false>      closest hit over the compressed 8-wide BVH (prt_bvh8.cuh).  Persistent warps pull ray
+//                            records from the queue in chunks; a lane whose ray is finished retires it and takes the
+//                            next one, so the heavy-tailed traversal length of an incoherent ray no longer idles the
+//                            other 31 lanes.  Retiring appends the path to the shading queue of the material it hit
+//                            (warp ballot + one atomic); the triangle record carries that queue and its own index, so
+//                            retiring costs no dependent loads.
 //     k_wf_shade<queue>      one thread per queued path: rebuilds the surface interaction from (t, b1, b2, id), runs
-//                            pt_shade, appends the shadow-ray request to the shadow queue and the surviving path to
-//                            the next bounce's extend queue (both ballot-compacted)
+//                            pt_shade, appends the shadow-ray record to the shadow queue and the next ray's record to
+//                            the next bounce's extend queue (both ballot-compacted, so records are dense and a warp's
+//                            refill reads consecutive 16-byte words).  Everything a ray needs in the traversal loop
+//                            (origin, reciprocal direction, the shear constants of the watertight triangle test) is
+//                            precomputed HERE, where all 32 lanes are busy, not in the trace kernel's refill path.
 //     k_wf_trace<true>       shadow rays (any hit), same dynamic fetch; unoccluded ones add their NEE term
 //   k_wf_film                one CTA per 16 x 16 pixel tile splats the tile's finished samples into shared memory
 //                            (tent filter) and adds the tile to the film
@@ -36,20 +40,38 @@ static constexpr int WF_CSTRIDE = 16;      // ints per bounce in the counter arr
 static constexpr int WF_CHUNK = 64;        // rays a warp reserves per atomic on the queue head
 static constexpr int WF_TRACE_THREADS = 128;
 static constexpr int WF_SHADE_THREADS = 256;
+#ifndef WF_SHADE_MINB
+#define WF_SHADE_MINB 2                   // min resident CTAs per SM the shading kernels are compiled for
+#endif
+#ifndef WF_COOP_MAX
+#define WF_COOP_MAX 12                     // warp-cooperative triangle tests while at most this many lanes hold triangles
+#endif
+#ifndef WF_REFILL_MIN
+#define WF_REFILL_MIN 1                    // idle lanes before a warp goes back to the queue
+#endif
+#ifndef WF_TRACE_MINB
+#define WF_TRACE_MINB 8                   // min resident CTAs per SM the trace kernels are compiled for
+#endif
 enum { C_EXT = 0, C_MAT = 1, C_SH = 4, C_HEAD_EXT = 8, C_HEAD_SH = 12 };
 
+// ray record, 4 x float4, written by the producer at the ray's queue position:
+//   r0 = origin xyz, bits(path slot)          r1 = direction xyz, tmax
+//   r2 = 1/direction xyz (clamped, bvh8_ray), extra (shadow rays: MIS weight)
+//   r3 = Sx, Sy, Sz, bits(kx | ky << 2 | kz << 4)     (ray_precompute: watertight triangle test)
+struct WfRays {
+    float4 *r0, *r1, *r2, *r3;
+};
+
 struct WfBuf {
-    float4 *S0;      // o.xyz, px
-    float4 *S1;      // d.xyz, py
-    float4 *S2;      // throughput rgb, eta
-    float4 *S3;      // radiance rgb, prev_pdf
-    float4 *S4;      // prev_p.xyz, bits(depth | prev_delta << 16)
-    uint4  *RNG;     // pcg32 state, inc
-    float4 *HIT;     // t, b1, b2, bits(id): id < 0 miss, < n_prims analytic primitive, else n_prims + sorted triangle
-    float4 *SH0;     // shadow ray o.xyz, tmax        (indexed by shadow-queue position)
-    float4 *SH1;     // shadow ray d.xyz, mis weight
-    float4 *SH2;     // contribution rgb, bits(slot)
-    uint32_t *q_ext[2];
+    // path state: one 128-byte record (= one cache line) per slot, so the shading kernels' random access by slot
+    // costs one line instead of seven sectors in seven lines
+    //   [0] o.xyz, px   [1] d.xyz, py   [2] throughput rgb, eta   [3] radiance rgb, prev_pdf
+    //   [4] prev_p.xyz, bits(depth | prev_delta << 16)   [5] pcg32 state, inc
+    //   [6] hit: t, b1, b2, bits(id) (id < 0 miss, < n_prims analytic primitive, else n_prims + sorted triangle)
+    float4 *ST;
+    WfRays ext[2];   // extend rays of bounce b live in ext[b & 1]
+    WfRays sh;       // shadow rays of the current bounce
+    float4 *SHC;     // shadow rays: NEE contribution rgb
     uint32_t *q_mat[WF_QUEUES];
     int *cnt;        // [bounces + 1][WF_CSTRIDE]
     uint32_t cap, L, n_layers, j0;
@@ -72,9 +94,20 @@ __device__ __forceinline__ int wf_reserve(int *counter, bool pred) {
     return pred ? base + __popc(m & lanemask_lt()) : -1;
 }
 
+__device__ __forceinline__ void wf_write_ray(const WfRays &R, int pos, float3 o, float3 d, float tmax, uint32_t slot, float extra) {
+    const RayPre rp = ray_precompute(d);
+    const Bvh8Ray r8 = bvh8_ray(o, d);
+    R.r0[pos] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
+    R.r1[pos] = make_float4(d.x, d.y, d.z, tmax);
+    R.r2[pos] = make_float4(r8.inv.x, r8.inv.y, r8.inv.z, extra);
+    R.r3[pos] = make_float4(rp.Sx, rp.Sy, rp.Sz, __int_as_float(rp.kx | (rp.ky << 2) | (rp.kz << 4)));
+}
+
 __device__ __forceinline__ void wf_load_state(const WfBuf &B, uint32_t slot, PtState &st) {
-    float4 a = B.S0[slot], b = B.S1[slot], c = B.S2[slot], d = B.S3[slot], e = B.S4[slot];
-    uint4 r = B.RNG[slot];
+    const float4 *rec = B.ST + 8 * (size_t) slot;
+    float4 a = rec[0], b = rec[1], c = rec[2], d = rec[3], e = rec[4];
+    const float4 rr = rec[5];
+    uint4 r = make_uint4(__float_as_uint(rr.x), __float_as_uint(rr.y), __float_as_uint(rr.z), __float_as_uint(rr.w));
     st.o = xyz(a); st.px = a.w;
     st.d = xyz(b); st.py = b.w;
     st.thr = xyz(c); st.eta = c.w;
@@ -88,12 +121,14 @@ __device__ __forceinline__ void wf_load_state(const WfBuf &B, uint32_t slot, PtS
 }
 
 __device__ __forceinline__ void wf_store_state(const WfBuf &B, uint32_t slot, const PtState &st) {
-    B.S0[slot] = make_float4(st.o.x, st.o.y, st.o.z, st.px);
-    B.S1[slot] = make_float4(st.d.x, st.d.y, st.d.z, st.py);
-    B.S2[slot] = make_float4(st.thr.x, st.thr.y, st.thr.z, st.eta);
-    B.S3[slot] = make_float4(st.res.x, st.res.y, st.res.z, st.prev_pdf);
-    B.S4[slot] = make_float4(st.prev_p.x, st.prev_p.y, st.prev_p.z, __int_as_float(st.depth | ((int) st.prev_delta << 16)));
-    B.RNG[slot] = make_uint4((uint32_t) st.rng.state, (uint32_t) (st.rng.state >> 32), (uint32_t) st.rng.inc, (uint32_t) (st.rng.inc >> 32));
+    float4 *rec = B.ST + 8 * (size_t) slot;
+    rec[0] = make_float4(st.o.x, st.o.y, st.o.z, st.px);
+    rec[1] = make_float4(st.d.x, st.d.y, st.d.z, st.py);
+    rec[2] = make_float4(st.thr.x, st.thr.y, st.thr.z, st.eta);
+    rec[3] = make_float4(st.res.x, st.res.y, st.res.z, st.prev_pdf);
+    rec[4] = make_float4(st.prev_p.x, st.prev_p.y, st.prev_p.z, __int_as_float(st.depth | ((int) st.prev_delta << 16)));
+    rec[5] = make_float4(__uint_as_float((uint32_t) st.rng.state), __uint_as_float((uint32_t) (st.rng.state >> 32)),
+                         __uint_as_float((uint32_t) st.rng.inc), __uint_as_float((uint32_t) (st.rng.inc >> 32)));
 }
 
 // slot -> pixel: a layer (one sample of every pixel) is laid out tile by tile, 256 slots per 16 x 16 tile, and the 32
@@ -119,24 +154,26 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_generate(const PtDev P,
         const uint32_t layer = slot / B.L, r = slot - layer * B.L;
         int x, y;
         const bool inside = wf_slot_pixel(P, r, x, y);
+        PtState st;
         if (inside) {
-            PtState st;
             pt_init(P, x, y, P.s_offset + (B.j0 + layer) * P.s_stride, st);
             wf_store_state(B, slot, st);
             made++;
         }
         const int q = wf_reserve(B.cnt + C_EXT, inside);
-        if (inside) B.q_ext[0][q] = slot;
+        if (inside) wf_write_ray(B.ext[0], q, st.o, st.d, PRT_INF, slot, 0.0f);
     }
     wf_add_stat(P, 0, made);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// ray queries with dynamic fetch
+// ray queries with dynamic fetch over the compressed 8-wide BVH
 // ------------------------------------------------------------------------------------------------------------------
-template <bool ANY, bool W8>
-__global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(const PtDev P, const WfBuf B, const int bounce) {
+template <bool ANY>
+__global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(const PtDev P, const WfBuf B, const int bounce) {
     __shared__ DPrim sprims[MAX_SMEM_PRIMS];
+    __shared__ int s_owner[WF_TRACE_THREADS], s_win[WF_TRACE_THREADS];
+    __shared__ unsigned s_tmin[WF_TRACE_THREADS];
     const DScene &sc = P.sc;
     const DPrim *prims = sprims;
     if (sc.n_prims > MAX_SMEM_PRIMS) prims = sc.prims;
@@ -149,75 +186,68 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(const PtDev P, co
     int *C = B.cnt + bounce * WF_CSTRIDE;
     const int n = ANY ? C[C_SH] : C[C_EXT];
     int *head = C + (ANY ? C_HEAD_SH : C_HEAD_EXT);
-    const uint32_t *queue = B.q_ext[bounce & 1];
+    const WfRays R = ANY ? B.sh : B.ext[bounce & 1];
     const int lane = threadIdx.x & 31;
-    const int DONE = 0x7fffffff;
+    int *so = s_owner + (threadIdx.x & ~31), *sw = s_win + (threadIdx.x & ~31);
+    unsigned *stm = s_tmin + (threadIdx.x & ~31);
 
     int pool_next = 0, pool_end = 0;     // warp-uniform: queue positions this warp has reserved
     bool dry = false;                    // warp-uniform: the queue is exhausted
-    bool has = false;
-    uint32_t slot = 0;                   // path slot (closest) / shadow-queue position (any)
-    float3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
-    RayPre rp = ray_precompute(d);
+    bool has = false, busy = false;      // lane holds a ray / its traversal is still running
+    uint32_t slot = 0, qpos = 0;         // path slot, queue position of the ray
+    Bvh8Ray r8;
+    r8.o = mk3(0, 0, 0); r8.inv = mk3(1, 1, 1); r8.octinv4 = 0;
+    RayPre rp;
+    rp.kx = 0; rp.ky = 1; rp.kz = 2; rp.Sx = rp.Sy = 0.0f; rp.Sz = 1.0f;
+    int kpack = 0;
     float tbest = 0.0f, b1 = 0.0f, b2 = 0.0f, prim_t = 0.0f;
-    int best = -1, best_prim = -1, sp = 0;
-    // BVH2 state (W8 == false)
-    float3 inv = mk3(0, 0, 0);
-    int ref = DONE;
-    int   stack_ref[W8 ? 1 : PRT_STACK];
-    float stack_t[W8 ? 1 : PRT_STACK];
-    // BVH8 state (W8 == true): current node group (child base, hit bits | imask), its triangle group, stack of groups
-    Bvh8Ray r8 = bvh8_ray(o, d);
-    uint2 ng = make_uint2(0, 0);
-    uint2 gstack[W8 ? BVH8_STACK : 1];
-    bool busy = false;
+    int best = -1, best_prim = -1, sp = 0;      // best: (sorted triangle << 2) | shading queue, or -1
+    uint2 ng = make_uint2(0, 0);                // node group in hand: child base, hit bits | imask
+    uint2 gstack[BVH8_STACK];
     unsigned n_rays = 0, n_valid = 0;
 
     for (;;) {
         // ---- retire finished rays ----
-        const bool fin = has && (W8 ? !busy : ref == DONE);
+        const bool fin = has && !busy;
         if (__any_sync(FULL, fin)) {
             if (!ANY) {
                 int qi = -1;
                 if (fin) {
-                    int id = -1, material = 0;
+                    int id = -1;
                     float t = tbest;
                     if (best >= 0 && (best_prim < 0 || tbest < prim_t)) {
-                        const int sorted = W8 ? (int) __ldg(sc.tri8_sorted + best) : best;
-                        id = sc.n_prims + sorted;
-                        material = __ldg(&sc.tri_info[sorted].z);
+                        id = sc.n_prims + (best >> 2);
+                        qi = best & 3;
                     } else if (best_prim >= 0) {
                         id = best_prim;
                         t = prim_t;
-                        material = prims[best_prim].material;
-                    }
-                    B.HIT[slot] = make_float4(t, b1, b2, __int_as_float(id));
-                    if (id >= 0) {
-                        const int kind = __ldg(&sc.mats[material].kind);
+                        const int kind = __ldg(&sc.mats[prims[best_prim].material].kind);
                         qi = kind == PRT_MAT_DIFFUSE ? 0 : (kind == PRT_MAT_DIELECTRIC ? 1 : 2);
-                        n_valid++;
                     }
+                    B.ST[8 * (size_t) slot + 6] = make_float4(t, b1, b2, __int_as_float(id));
+                    if (id >= 0) n_valid++;
                 }
 #pragma unroll
                 for (int k = 0; k < WF_QUEUES; k++) {
                     const int q = wf_reserve(C + C_MAT + k, qi == k);
                     if (qi == k) B.q_mat[k][q] = slot;
                 }
-            } else if (fin && best < 0) {
-                const float4 c = B.SH2[slot];
-                const float w = B.SH1[slot].w;
-                const uint32_t ps = (uint32_t) __float_as_int(c.w);
-                float4 r = B.S3[ps];
+            } else if (fin && best < 0 && best_prim < 0) {
+                const float4 c = B.SHC[qpos];
+                const float w = R.r2[qpos].w;
+                float4 *acc = B.ST + 8 * (size_t) slot + 3;
+                float4 r = *acc;
                 r.x = fmaf(c.x, w, r.x);
                 r.y = fmaf(c.y, w, r.y);
                 r.z = fmaf(c.z, w, r.z);
-                B.S3[ps] = r;
+                *acc = r;
             }
             if (fin) has = false;
         }
         // ---- refill idle lanes ----
         if (!dry) {
             unsigned need = __ballot_sync(FULL, !has);
+            if (__popc(need) < WF_REFILL_MIN && need != FULL && __any_sync(FULL, busy)) need = 0;
             while (need) {
                 if (pool_next == pool_end) {
                     int base = 0;
@@ -235,47 +265,40 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(const PtDev P, co
                 const int rank = __popc(need & lanemask_lt());
                 const bool take = !has && rank < avail;
                 if (take) {
-                    const int idx = pool_next + rank;
-                    if (!ANY) {
-                        slot = queue[idx];
-                        const float4 a = B.S0[slot], bb = B.S1[slot];
-                        o = xyz(a);
-                        d = xyz(bb);
-                        tbest = PRT_INF;
-                    } else {
-                        slot = (uint32_t) idx;
-                        const float4 a = B.SH0[idx], bb = B.SH1[idx];
-                        o = xyz(a);
-                        d = xyz(bb);
-                        tbest = a.w;
-                    }
+                    qpos = (uint32_t) (pool_next + rank);
+                    const float4 a = R.r0[qpos], c2 = R.r2[qpos], c3 = R.r3[qpos];
+                    r8.o = xyz(a);
+                    slot = __float_as_uint(a.w);
+                    r8.inv = xyz(c2);
+                    const uint32_t oct = (c2.x < 0.0f ? 4u : 0u) | (c2.y < 0.0f ? 2u : 0u) | (c2.z < 0.0f ? 1u : 0u);
+                    r8.octinv4 = (7u - oct) * 0x01010101u;
+                    rp.Sx = c3.x; rp.Sy = c3.y; rp.Sz = c3.z;
+                    kpack = __float_as_int(c3.w);
+                    rp.kx = kpack & 3; rp.ky = (kpack >> 2) & 3; rp.kz = (kpack >> 4) & 3;
                     has = true;
                     n_rays++;
                     best = -1;
                     best_prim = -1;
-                    prim_t = tbest;
+                    tbest = PRT_INF;
                     bool blocked = false;
-                    for (int i = 0; i < sc.n_prims; i++) {
-                        const float t = intersect_prim(prims[i], o, d, prim_t);
-                        if (t >= 0.0f && (best_prim < 0 || t < prim_t)) {
-                            best_prim = i;
-                            prim_t = t;
-                            if (ANY) blocked = true;
+                    if (sc.n_prims > 0 || ANY) {
+                        const float4 bb = R.r1[qpos];
+                        tbest = bb.w;
+                        prim_t = tbest;
+                        const float3 d = xyz(bb);
+                        for (int i = 0; i < sc.n_prims; i++) {
+                            const float t = intersect_prim(prims[i], r8.o, d, prim_t);
+                            if (t >= 0.0f && (best_prim < 0 || t < prim_t)) {
+                                best_prim = i;
+                                prim_t = t;
+                                if (ANY) blocked = true;
+                            }
                         }
+                        if (!ANY) tbest = prim_t;
                     }
-                    if (!ANY) tbest = prim_t;
-                    rp = ray_precompute(d);
                     sp = 0;
-                    const bool go = !(sc.n_tris == 0 || blocked);
-                    if (W8) {
-                        r8 = bvh8_ray(o, d);
-                        ng = make_uint2(0u, 0x80000000u);
-                        busy = go;
-                    } else {
-                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                        ref = go ? sc.root_ref : DONE;
-                    }
-                    if (ANY && blocked) best = 0;
+                    ng = make_uint2(0u, 0x80000000u);
+                    busy = !(sc.n_tris == 0 || blocked);
                 }
                 pool_next += min(avail, __popc(need));
                 need = __ballot_sync(FULL, !has);
@@ -283,86 +306,100 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(const PtDev P, co
         }
         if (!__any_sync(FULL, has)) break;
 
-        if (W8) {
-            // ---- one wide node per lane and iteration, then the triangles it yielded ----
-            if (busy) {
-                uint2 tg = make_uint2(0u, 0u);
-                if (ng.y > 0x00ffffffu) {
-                    const uint32_t hits = ng.y, imask8 = ng.y & 0xffu;
-                    const int bit = 31 - __clz(hits);
-                    ng.y &= ~(1u << bit);
-                    if (ng.y > 0x00ffffffu && sp < BVH8_STACK) gstack[sp++] = ng;
-                    const uint32_t slot_index = (uint32_t) (bit - 24) ^ (r8.octinv4 & 0xffu);
-                    const uint32_t rel = __popc(imask8 & ~(0xffffffffu << slot_index));
-                    uint32_t child_base, tri_base, imask;
-                    const uint32_t hm = bvh8_node(sc.nodes8, ng.x + rel, r8, tbest, child_base, tri_base, imask);
-                    ng = make_uint2(child_base, (hm & 0xff000000u) | imask);
-                    tg = make_uint2(tri_base, hm & 0x00ffffffu);
+        // ---- one wide node per lane and iteration ----
+        uint2 tg = make_uint2(0u, 0u);
+        if (busy && ng.y > 0x00ffffffu) {
+            const uint32_t hits = ng.y, imask8 = ng.y & 0xffu;
+            const int bit = 31 - __clz(hits);
+            ng.y &= ~(1u << bit);
+            if (ng.y > 0x00ffffffu && sp < BVH8_STACK) gstack[sp++] = ng;
+            const uint32_t slot_index = (uint32_t) (bit - 24) ^ (r8.octinv4 & 0xffu);
+            const uint32_t rel = __popc(imask8 & ~(0xffffffffu << slot_index));
+            uint32_t child_base, tri_base, imask;
+            const uint32_t hm = bvh8_node(sc.nodes8, ng.x + rel, r8, tbest, child_base, tri_base, imask);
+            ng = make_uint2(child_base, (hm & 0xff000000u) | imask);
+            tg = make_uint2(tri_base, hm & 0x00ffffffu);
+        }
+        // ---- the triangles those nodes yielded ----
+        const unsigned mT = __ballot_sync(FULL, tg.y != 0u);
+        if (__popc(mT) > WF_COOP_MAX) {
+            // most lanes hold triangles (small scenes, coherent rays): every lane walks its own list
+            while (tg.y) {
+                const int bit = 31 - __clz(tg.y);
+                tg.y &= ~(1u << bit);
+                const float4 *tv = sc.tri_v8 + 3 * (size_t) (tg.x + (uint32_t) bit);
+                const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
+                if (intersect_tri_wt(rp, r8.o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+                    best = __float_as_int(b.w);
+                    if (ANY) { busy = false; break; }
                 }
-                while (tg.y) {
-                    const int bit = 31 - __clz(tg.y);
-                    tg.y &= ~(1u << bit);
-                    const uint32_t ti = tg.x + (uint32_t) bit;
-                    const float4 *tv = sc.tri_v8 + 3 * (size_t) ti;
+            }
+        } else if (mT) {
+            // A few lanes hold several triangles each and most hold none (the per-lane loop ran with 4.5 of 32 lanes
+            // on incoherent rays).  The warp's (ray, triangle) pairs are numbered by a prefix sum and dealt out one
+            // per lane: a lane pulls the owning ray through shuffles, tests its triangle, and the closest hit per
+            // owner is chosen with two shared-memory atomics (distance first, then the lowest pair).
+            const unsigned cnt = __popc(tg.y);
+            unsigned incl = cnt;
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                const unsigned v = __shfl_up_sync(FULL, incl, k);
+                if (lane >= k) incl += v;
+            }
+            const unsigned total = __shfl_sync(FULL, incl, 31), off = incl - cnt;
+            for (unsigned base = 0; base < total; base += 32) {
+                {
+                    const unsigned k0 = max(off, base), k1 = min(off + cnt, base + 32u);
+                    for (unsigned k = k0; k < k1; k++) so[k - base] = lane;
+                }
+                stm[lane] = 0xffffffffu;
+                sw[lane] = 32;
+                __syncwarp();
+                const unsigned p = base + lane;
+                const bool valid = p < total;
+                const int own = valid ? so[lane] : lane;
+                const unsigned o_off = __shfl_sync(FULL, off, own), o_mask = __shfl_sync(FULL, tg.y, own);
+                const unsigned o_base = __shfl_sync(FULL, tg.x, own);
+                const float3 ro = mk3(__shfl_sync(FULL, r8.o.x, own), __shfl_sync(FULL, r8.o.y, own), __shfl_sync(FULL, r8.o.z, own));
+                RayPre q;
+                q.Sx = __shfl_sync(FULL, rp.Sx, own);
+                q.Sy = __shfl_sync(FULL, rp.Sy, own);
+                q.Sz = __shfl_sync(FULL, rp.Sz, own);
+                const int kp = __shfl_sync(FULL, kpack, own);
+                q.kx = kp & 3; q.ky = (kp >> 2) & 3; q.kz = (kp >> 4) & 3;
+                float ht = __shfl_sync(FULL, tbest, own), hb1 = 0.0f, hb2 = 0.0f;
+                int hid = -1;
+                bool hit = false;
+                if (valid) {
+                    unsigned m = o_mask;
+                    for (unsigned r = p - o_off; r; r--) m &= m - 1u;
+                    const float4 *tv = sc.tri_v8 + 3 * (size_t) (o_base + (uint32_t) (__ffs(m) - 1));
                     const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
-                    if (intersect_tri_wt(rp, o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
-                        best = (int) ti;
-                        if (ANY) { busy = false; break; }
-                    }
+                    hit = intersect_tri_wt(q, ro, xyz(a), xyz(b), xyz(c), ht, hb1, hb2);
+                    hid = __float_as_int(b.w);
+                    ht += 0.0f;
+                    if (hit) atomicMin(&stm[own], __float_as_uint(ht));
                 }
-                if (busy && ng.y <= 0x00ffffffu) {
-                    if (sp > 0) ng = gstack[--sp];
-                    else busy = false;
+                __syncwarp();
+                if (hit && __float_as_uint(ht) == stm[own]) atomicMin(&sw[own], lane);
+                __syncwarp();
+                const int wl = sw[lane];
+                const int srcl = wl < 32 ? wl : lane;
+                const float wt = __shfl_sync(FULL, ht, srcl), wb1 = __shfl_sync(FULL, hb1, srcl), wb2 = __shfl_sync(FULL, hb2, srcl);
+                const int wid = __shfl_sync(FULL, hid, srcl);
+                if (wl < 32) {
+                    tbest = wt;
+                    b1 = wb1;
+                    b2 = wb2;
+                    best = wid;
+                    if (ANY) busy = false;
                 }
+                __syncwarp();
             }
-        } else {
-#define PRT_POP()                                                        \
-    do {                                                                 \
-        ref = DONE;                                                      \
-        while (sp > 0) {                                                 \
-            --sp;                                                        \
-            if (stack_t[sp] <= tbest) { ref = stack_ref[sp]; break; }    \
-        }                                                                \
-    } while (0)
-            // ---- inner nodes: every lane descends until it holds a leaf or is done ----
-            while ((unsigned) ref < (unsigned) DONE) {
-                const float4 *nd = sc.nodes + 4 * (size_t) ref;
-                const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
-                const float tl = box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tbest);
-                const float tr = box_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, inv, tbest);
-                const int rl = __float_as_int(q3.x), rr = __float_as_int(q3.y);
-                const bool hl = tl < PRT_INF, hr = tr < PRT_INF;
-                if (hl && hr) {
-                    const bool lf = tl <= tr;
-                    if (sp < PRT_STACK) {
-                        stack_ref[sp] = lf ? rr : rl;
-                        stack_t[sp] = lf ? tr : tl;
-                        sp++;
-                    }
-                    ref = lf ? rl : rr;
-                } else if (hl || hr) {
-                    ref = hl ? rl : rr;
-                } else {
-                    PRT_POP();
-                }
-            }
-            // ---- leaf ----
-            if (ref < 0) {
-                const int code = ~ref;
-                const int first = code >> 2, count = (code & 3) + 1;
-                bool stop = false;
-                for (int j = 0; j < count; j++) {
-                    const float4 *tv = sc.tri_v + 3 * (size_t) (first + j);
-                    const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
-                    if (intersect_tri_wt(rp, o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
-                        best = first + j;
-                        if (ANY) { stop = true; break; }
-                    }
-                }
-                if (stop) ref = DONE;
-                else PRT_POP();
-            }
-#undef PRT_POP
+        }
+        if (busy && ng.y <= 0x00ffffffu) {
+            if (sp > 0) ng = gstack[--sp];
+            else busy = false;
         }
     }
     wf_add_stat(P, 2, n_rays);
@@ -374,23 +411,23 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(const PtDev P, co
 // shading, one kernel per material queue
 // ------------------------------------------------------------------------------------------------------------------
 template <int QI>
-__global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade(const PtDev P, const WfBuf B, const int bounce) {
+__global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(const PtDev P, const WfBuf B, const int bounce) {
     int *C = B.cnt + bounce * WF_CSTRIDE;
     int *Cn = C + WF_CSTRIDE;
     const int n = C[C_MAT + QI];
     const uint32_t *q = B.q_mat[QI];
-    uint32_t *qn = B.q_ext[(bounce + 1) & 1];
+    const WfRays Rn = B.ext[(bounce + 1) & 1];
     for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
         const int i = i0 + threadIdx.x;
         bool live = false;
         uint32_t slot = 0;
         ShadowReq sr;
         sr.want = false;
+        PtState st;
         if (i < n) {
             slot = q[i];
-            PtState st;
             wf_load_state(B, slot, st);
-            const float4 hv = B.HIT[slot];
+            const float4 hv = B.ST[8 * (size_t) slot + 6];
             const int id = __float_as_int(hv.w);
             Hit h;
             if (id >= P.sc.n_prims) fill_tri_hit(P.sc, id - P.sc.n_prims, hv.x, hv.y, hv.z, h);
@@ -400,12 +437,11 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade(const PtDev P, co
         }
         const int j = wf_reserve(C + C_SH, sr.want);
         if (sr.want) {
-            B.SH0[j] = make_float4(sr.o.x, sr.o.y, sr.o.z, sr.tmax);
-            B.SH1[j] = make_float4(sr.d.x, sr.d.y, sr.d.z, sr.w);
-            B.SH2[j] = make_float4(sr.c.x, sr.c.y, sr.c.z, __int_as_float((int) slot));
+            wf_write_ray(B.sh, j, sr.o, sr.d, sr.tmax, slot, sr.w);
+            B.SHC[j] = make_float4(sr.c.x, sr.c.y, sr.c.z, 0.0f);
         }
         const int e = wf_reserve(Cn + C_EXT, live);
-        if (live) qn[e] = slot;
+        if (live) wf_write_ray(Rn, e, st.o, st.d, PRT_INF, slot, 0.0f);
     }
 }
 
@@ -423,8 +459,9 @@ __global__ void __launch_bounds__(256) k_wf_film(const PtDev P, const WfBuf B) {
     if (wf_slot_pixel(P, r, x, y)) {
         for (uint32_t layer = 0; layer < B.n_layers; layer++) {
             const uint32_t slot = layer * B.L + r;
-            const float px = B.S0[slot].w, py = B.S1[slot].w;
-            const float4 res = B.S3[slot];
+            const float4 *rec = B.ST + 8 * (size_t) slot;
+            const float px = rec[0].w, py = rec[1].w;
+            const float4 res = rec[3];
             pt_splat(P.tent, tile, tx0, ty0, px, py, xyz(res));
         }
     }
@@ -441,6 +478,7 @@ static int wf_grid(prt_context *c, const void *kernel, int threads, int *grid) {
 }
 
 int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
+    PRT_REQUIRE(P.sc.n_tris == 0 || P.sc.n_nodes8 > 0, "render_path (wavefront): the scene has no 8-wide BVH");
     const uint32_t n_tiles = (uint32_t) P.tiles_x * (uint32_t) P.tiles_y;
     const uint64_t L = (uint64_t) n_tiles * 256u;
     uint64_t batch = 1ull << 24;
@@ -454,9 +492,9 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
     const uint64_t cap = layers * L;
     PRT_REQUIRE(cap < (1ull << 31), "render_path (wavefront): batch too large");
     const int bounces = P.max_depth > 1 ? P.max_depth : 1;
-    const size_t cnt_bytes = sizeof(int) * WF_CSTRIDE * (size_t) (bounces + 1);
-    const size_t per_slot = 16 * 10 + 4 * (2 + WF_QUEUES);
-    const size_t need = (size_t) cap * per_slot + ((cnt_bytes + 255) & ~(size_t) 255);
+    const size_t cnt_bytes = (sizeof(int) * WF_CSTRIDE * (size_t) (bounces + 1) + 255) & ~(size_t) 255;
+    const size_t per_slot = 16 * (8 + 8 + 4 + 1) + 4 * WF_QUEUES;
+    const size_t need = (size_t) cap * per_slot + cnt_bytes;
     if (need > c->wf_cap) {
         if (c->wf_dev) cudaFree(c->wf_dev);
         c->wf_dev = nullptr;
@@ -468,18 +506,12 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
     {
         char *p = reinterpret_cast<char *>(c->wf_dev);
         auto take = [&](size_t bytes) { char *r = p; p += bytes; return r; };
-        B.cnt = reinterpret_cast<int *>(take((cnt_bytes + 255) & ~(size_t) 255));
-        B.S0 = reinterpret_cast<float4 *>(take(16 * cap));
-        B.S1 = reinterpret_cast<float4 *>(take(16 * cap));
-        B.S2 = reinterpret_cast<float4 *>(take(16 * cap));
-        B.S3 = reinterpret_cast<float4 *>(take(16 * cap));
-        B.S4 = reinterpret_cast<float4 *>(take(16 * cap));
-        B.RNG = reinterpret_cast<uint4 *>(take(16 * cap));
-        B.HIT = reinterpret_cast<float4 *>(take(16 * cap));
-        B.SH0 = reinterpret_cast<float4 *>(take(16 * cap));
-        B.SH1 = reinterpret_cast<float4 *>(take(16 * cap));
-        B.SH2 = reinterpret_cast<float4 *>(take(16 * cap));
-        for (int k = 0; k < 2; k++) B.q_ext[k] = reinterpret_cast<uint32_t *>(take(4 * cap));
+        auto take4 = [&]() { return reinterpret_cast<float4 *>(take(16 * cap)); };
+        B.cnt = reinterpret_cast<int *>(take(cnt_bytes));
+        B.ST = reinterpret_cast<float4 *>(take(128 * cap));
+        for (int k = 0; k < 2; k++) { B.ext[k].r0 = take4(); B.ext[k].r1 = take4(); B.ext[k].r2 = take4(); B.ext[k].r3 = take4(); }
+        B.sh.r0 = take4(); B.sh.r1 = take4(); B.sh.r2 = take4(); B.sh.r3 = take4();
+        B.SHC = take4();
         for (int k = 0; k < WF_QUEUES; k++) B.q_mat[k] = reinterpret_cast<uint32_t *>(take(4 * cap));
     }
     B.cap = (uint32_t) cap;
@@ -487,13 +519,8 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
     int g_gen = 1, g_ext = 1, g_sh = 1, g_shade[WF_QUEUES] = { 1, 1, 1 };
     int rc;
     if ((rc = wf_grid(c, (const void *) k_wf_generate, WF_SHADE_THREADS, &g_gen))) return rc;
-    // BVH8c by default when it exists; PRT_BVH=2 keeps the binary tree (A/B runs, parity tests between the two)
-    const char *bsel = getenv("PRT_BVH");
-    const bool w8 = P.sc.n_nodes8 > 0 && !(bsel && bsel[0] == '2');
-    const void *k_ext = w8 ? (const void *) k_wf_trace<false, true> : (const void *) k_wf_trace<false, false>;
-    const void *k_sh = w8 ? (const void *) k_wf_trace<true, true> : (const void *) k_wf_trace<true, false>;
-    if ((rc = wf_grid(c, k_ext, WF_TRACE_THREADS, &g_ext))) return rc;
-    if ((rc = wf_grid(c, k_sh, WF_TRACE_THREADS, &g_sh))) return rc;
+    if ((rc = wf_grid(c, (const void *) k_wf_trace<false>, WF_TRACE_THREADS, &g_ext))) return rc;
+    if ((rc = wf_grid(c, (const void *) k_wf_trace<true>, WF_TRACE_THREADS, &g_sh))) return rc;
     if ((rc = wf_grid(c, (const void *) k_wf_shade<0>, WF_SHADE_THREADS, &g_shade[0]))) return rc;
     if ((rc = wf_grid(c, (const void *) k_wf_shade<1>, WF_SHADE_THREADS, &g_shade[1]))) return rc;
     if ((rc = wf_grid(c, (const void *) k_wf_shade<2>, WF_SHADE_THREADS, &g_shade[2]))) return rc;
@@ -505,8 +532,7 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
         k_wf_generate<<<g_gen, WF_SHADE_THREADS, 0, st>>>(P, B);
         launches++;
         for (int b = 0; b < bounces; b++) {
-            if (w8) k_wf_trace<false, true><<<g_ext, WF_TRACE_THREADS, 0, st>>>(P, B, b);
-            else k_wf_trace<false, false><<<g_ext, WF_TRACE_THREADS, 0, st>>>(P, B, b);
+            k_wf_trace<false><<<g_ext, WF_TRACE_THREADS, 0, st>>>(P, B, b);
             launches++;
             if (P.kind_mask & (1u << PRT_MAT_DIFFUSE)) { k_wf_shade<0><<<g_shade[0], WF_SHADE_THREADS, 0, st>>>(P, B, b); launches++; }
             if (P.kind_mask & (1u << PRT_MAT_DIELECTRIC)) { k_wf_shade<1><<<g_shade[1], WF_SHADE_THREADS, 0, st>>>(P, B, b); launches++; }
@@ -515,8 +541,7 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
                 launches++;
             }
             if (b + 1 < P.max_depth && (P.kind_mask & (1u << PRT_MAT_DIFFUSE)) && P.sc.n_emitters > 0) {
-                if (w8) k_wf_trace<true, true><<<g_sh, WF_TRACE_THREADS, 0, st>>>(P, B, b);
-                else k_wf_trace<true, false><<<g_sh, WF_TRACE_THREADS, 0, st>>>(P, B, b);
+                k_wf_trace<true><<<g_sh, WF_TRACE_THREADS, 0, st>>>(P, B, b);
                 launches++;
             }
         }
