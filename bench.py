@@ -120,21 +120,33 @@ def cpu_oracle_rate(desc, params, spp: int, seed: int, threads: int):
     return st, dt
 
 
-def run_pt(args, rank, world, local_rank):
-    """--workload cbox: BASELINE config 4 (scenes/cbox.xml at 2048^2, sample-sharded, one all-reduce of the film).
-    One step = one batch of `--spp` samples per pixel per GPU (the 4096-spp job is 256 such steps at 16 spp)."""
+def ncu_traffic(key: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json,
+    written by hand from profiles/*.txt); None when this workload has not been captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as fh:
+        d = json.load(fh)
+    e = d.get(key)
+    return (e["dram_bytes_per_launch"], e["source"]) if e else (None, None)
+
+
+WF_RAY_RECORD_BYTES = 64 + 16      # ray record read (4 x float4) + hit record written, per closest-hit query
+
+
+def pt_measure(args, workload, steps, warmup, rank, world, device, e2e_steps, cpu_baseline):
+    """One path-tracing workload (cbox = BASELINE config 4, heightfield = config 5) on an initialised process group.
+    One step = one batch of `spp` samples per pixel per GPU (the 4096-spp job is 256 such steps at 16 spp).
+    Returns the JSON line (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from prt_b200 import mi_compat as mi
     from prt_b200 import scenes
     from prt_b200.distributed import shard_samples
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    if args.workload.startswith("heightfield"):
+    if workload.startswith("heightfield"):
         # BASELINE config 5: 9 999 392-triangle height field in a closed box, 3840x2160, 8 diffuse bounces, no RR
-        n_side = int(args.workload.partition(":")[2] or 2237)
+        n_side = int(workload.partition(":")[2] or 2237)
         width, height = (3840, 2160) if args.res == 2048 else (args.res, args.res * 9 // 16)
         spp_step = args.spp if args.spp != C2_SPP else 2
         desc = scenes.heightfield_scene(n_side, (width, height), spp_step)
@@ -169,16 +181,17 @@ def run_pt(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(film, op=dist.ReduceOp.SUM)
 
-    for w in range(args.warmup):
+    for w in range(warmup):
         step(1000 + w)
     barrier()
     stats.zero_()
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(device.index)
     clocks.start()
     time.sleep(0.4)
     ev = []
     barrier()
-    for k in range(args.steps):
+    dev.ctx.profile_begin()                 # event pairs around every kernel group, on the launching stream
+    for k in range(steps):
         flush.fill_(k & 0xff)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record(stream)
@@ -193,8 +206,10 @@ def run_pt(args, rank, world, local_rank):
         ev.append(e)
     barrier()
     clk = clocks.stop()
+    classes = dev.ctx.profile_read()
     t_local = torch.tensor([sum(e[0].elapsed_time(e[3]) for e in ev)], dtype=torch.float64, device=device)
     kern_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    st_local = stats.cpu().numpy()
     st_all = stats.clone()
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
@@ -203,59 +218,91 @@ def run_pt(args, rank, world, local_rank):
     hs = st_all.cpu().numpy()
     paths, segments, rays, shadow = (int(x) for x in hs[:4])
     value = rays / (total_ms * 1e-3) / 1e6
-    # end to end: mi.render(scene) -> numpy image on the host
-    e2e_steps = args.e2e_steps or min(args.steps, 3)
-    integ.render(scene, seed=77, spp=spp_total)
+    # end to end: mi.render(scene) -> developed numpy image on the host (page-locked), every step
+    # warm-up: a caller holds the previous image while the next one renders, so the page-locked result pool needs two
+    # buffers before it reaches its steady state
+    keep = [integ.render(scene, seed=77, spp=spp_total), integ.render(scene, seed=78, spp=spp_total)]
+    del keep
     barrier()
     e2e_rays = 0
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         img = integ.render(scene, seed=2000 + k, spp=spp_total)
         e2e_rays += int(integ.last_stats["rays"])
-        checksum = float(img.mean())
+        checksum = float(img[::8, ::8].mean())         # touch the HOST result
     barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    peak, peak_src, _ = measured_peaks()
+    n_tris = desc.n_triangles()
+    # dominant kernel: the closest-hit trace kernel (one launch per bounce and batch); this rank's own counts
+    tc = classes.get("trace_closest", {"ms": 0.0, "launches": 0})
+    closest_local = int(st_local[2]) - int(st_local[3])
+    per_ray = bvh_min_bytes(n_tris) + WF_RAY_RECORD_BYTES
+    if tc["launches"]:
+        dom, dom_ms = "prt::k_wf_trace<false>", tc["ms"] / tc["launches"]
+        alg_bytes = closest_local * per_ray / tc["launches"]
+    else:                                              # PRT_PT_MODE=mega
+        mk = classes.get("megakernel", {"ms": kern_ms * steps, "launches": steps})
+        dom, dom_ms = "prt::k_render_path", mk["ms"] / max(mk["launches"], 1)
+        alg_bytes = int(st_local[2]) * bvh_min_bytes(n_tris) / max(mk["launches"], 1) + film.numel() * 4
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(workload.partition(":")[0])
+    n_launch = sum(c["launches"] for c in classes.values())
+    line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "msamples_per_s": paths / (total_ms * 1e-3) / 1e6,
+            "config": {"workload": wl_label,
+                       "spp_per_gpu_per_step": spp_step, "paths_per_gpu_per_step": width * height * n_s, "n_triangles": n_tris,
+                       "bvh": {"nodes": bvh["n_nodes"], "nodes8": bvh.get("n_nodes8"), "build_ms": bvh["build_ms"],
+                               "sah_cost": bvh["sah_cost"], "device_bytes": bvh["device_bytes"]},
+                       "n_analytic": desc.n_analytic(), "segments_per_path": segments / max(paths, 1),
+                       "rays_per_path": rays / max(paths, 1),
+                       "parallelism": f"sample-shards x{world}, BVH replicated, 1 NCCL all-reduce of {film.numel() * 4} B",
+                       "l2": "flushed between timed steps (384 MiB fill, untimed)"},
+            "e2e": {"value": e2e_rays / float(t_e2e.item()) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 512,
+                    "d2h_bytes_per_step": int(height * width * 3 * 4 + 64), "steps": e2e_steps,
+                    "api": "mi.render(scene) -> developed numpy image [H,W,3]", "host_checksum": checksum},
+            "gpu_launches": n_launch, "kernel": dom, "kernel_ms": dom_ms, "step_kernels_ms": kern_ms,
+            "kernel_classes": {k: {"ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] / steps,
+                                   "share": v["ms"] / max(sum(c["ms"] for c in classes.values()), 1e-9)}
+                               for k, v in classes.items()},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": f"dominant kernel {dom}: closest-hit rays x ({bvh_min_bytes(n_tris)} B B_min(N) of node + triangle "
+                                 f"fetches, SURVEY 8(d), + {WF_RAY_RECORD_BYTES} B ray/hit records) / its CUDA-event time; "
+                                 + ("scene lives on chip" if n_tris < 100000 else "scene >> L2: fetches go to HBM")},
+            "clocks": clk}
+    if cpu_baseline:
+        import orc_py
+        threads = os.cpu_count() or 1
+        cres, cspp = 256, 16                      # the cbox tutorial resolution, 16 spp: ~1 M paths
+        cdesc = scenes.cbox_scene(cres, cspp)
+        csc = mi.Scene(cdesc)
+        crp = csc.integrator().render_params(csc)
+        osc = orc_py.OracleScene(cdesc)
+        t0 = time.perf_counter()
+        _, cst = orc_py.render_path(osc, crp, seed=0, spp=cspp, prec=32, n_threads=threads)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": cst["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                                "sample": f"{cres}x{cres} x {cspp} spp of the same scene, oracle f32, {threads} threads, {dt:.1f} s"}
+    return line
+
+
+def run_pt(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    line = pt_measure(args, args.workload, args.steps, args.warmup, rank, world, device, args.e2e_steps or min(args.steps, 3),
+                      world == 1 and not args.no_cpu_baseline and not args.workload.startswith("heightfield"))
     if rank == 0:
-        peak, peak_src, _ = measured_peaks()
-        n_tris = desc.n_triangles()
-        rays_per_launch = rays / world / args.steps
-        alg_bytes = rays_per_launch * bvh_min_bytes(n_tris) + film.numel() * 4
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "msamples_per_s": paths / (total_ms * 1e-3) / 1e6,
-                "config": {"workload": wl_label,
-                           "spp_per_gpu_per_step": spp_step, "paths_per_gpu_per_step": width * height * n_s, "n_triangles": n_tris,
-                           "bvh": {"nodes": bvh["n_nodes"], "build_ms": bvh["build_ms"], "sah_cost": bvh["sah_cost"],
-                                   "device_bytes": bvh["device_bytes"]},
-                           "n_analytic": desc.n_analytic(), "segments_per_path": segments / max(paths, 1),
-                           "rays_per_path": rays / max(paths, 1),
-                           "parallelism": f"sample-shards x{world}, BVH replicated, 1 NCCL all-reduce of {film.numel() * 4} B",
-                           "l2": "flushed between timed steps (384 MiB fill, untimed)"},
-                "e2e": {"value": e2e_rays / float(t_e2e.item()) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 512,
-                        "d2h_bytes_per_step": int(film.numel() * 4 + 64), "steps": e2e_steps,
-                        "api": "mi.render(scene) -> numpy image", "host_checksum": checksum},
-                "gpu_launches": args.steps, "kernel": "prt::k_render_path", "kernel_ms": kern_ms,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                             "note": f"B_min(N) = {bvh_min_bytes(n_tris)} B/ray of node + triangle fetches (SURVEY 8(d)); "
-                                     + ("scene lives on chip" if n_tris < 100000 else "scene >> L2: fetches go to HBM")},
-                "clocks": clk}
-        if world == 1 and not args.no_cpu_baseline and not args.workload.startswith("heightfield"):
-            import orc_py
-            threads = os.cpu_count() or 1
-            cres, cspp = 256, 16                      # the cbox tutorial resolution, 16 spp: ~1 M paths
-            cdesc = scenes.cbox_scene(cres, cspp)
-            csc = mi.Scene(cdesc)
-            crp = csc.integrator().render_params(csc)
-            osc = orc_py.OracleScene(cdesc)
-            t0 = time.perf_counter()
-            _, cst = orc_py.render_path(osc, crp, seed=0, spp=cspp, prec=32, n_threads=threads)
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": cst["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                                    "sample": f"{cres}x{cres} x {cspp} spp of the same scene, oracle f32, {threads} threads, {dt:.1f} s"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -301,6 +348,7 @@ def main():
     ap.add_argument("--spp", type=int, default=C2_SPP, help="samples per (angle, element) per GPU and step")
     ap.add_argument("--res", type=int, default=2048, help="film resolution of the cbox workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the short cbox measurement appended to the default line")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: min(steps, 5))")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -364,6 +412,7 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     barrier()
+    dev.ctx.profile_begin()                         # event pair around every k_acquire launch, on the launching stream
     wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k & 0xff)                       # L2 flush between timed iterations (untimed)
@@ -381,6 +430,7 @@ def main():
     barrier()
     wall = time.perf_counter() - wall0
     clk = clocks.stop()
+    classes = dev.ctx.profile_read()
     step_ms = [e[0].elapsed_time(e[3]) for e in ev]
     kern_ms = [e[1].elapsed_time(e[2]) for e in ev]
     t_local = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
@@ -401,7 +451,8 @@ def main():
     so = sys.stdout
     sys.stdout = _quiet                              # the reference's method prints; keep ONE JSON line on stdout
     try:
-        integ.simulate_acquisition_parallel(scene)  # warm-up (allocates the pinned staging buffer)
+        integ.simulate_acquisition_parallel(scene)  # warm-up (allocates the pinned result buffers: the pool needs
+        integ.simulate_acquisition_parallel(scene)  # two, because the integrator still holds the previous result)
         barrier()
         e2e_rays = 0
         t0 = time.perf_counter()
@@ -427,12 +478,16 @@ def main():
     if rank == 0:
         peak, peak_src, sm_max = measured_peaks()
         n_tris = desc.n_triangles()
-        k_ms = float(np.mean(kern_ms))
-        rays_per_launch = rays / world / args.steps
+        k_ms = float(np.mean(kern_ms))             # all k_acquire launches of one step (one per steering angle)
+        acq = classes.get("acquire", {"ms": k_ms * args.steps, "launches": args.steps})
+        launch_ms = acq["ms"] / max(acq["launches"], 1)
+        rays_per_launch = rays / world / max(acq["launches"], 1)
         # algorithmic bytes per launch: BVH descent per ray (0 for analytic scenes, which live
-        # in shared memory) + the channel buffer written once (the megakernel streams no per-segment state)
-        alg_bytes = rays_per_launch * bvh_min_bytes(n_tris) + buf.numel() * 4
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        # in shared memory) + this launch's slice of the channel buffer written once (the megakernel streams no
+        # per-segment state)
+        alg_bytes = rays_per_launch * bvh_min_bytes(n_tris) + buf.numel() * 4 * args.steps / max(acq["launches"], 1)
+        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(args.workload)
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -447,12 +502,16 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "UltraIntegrator.simulate_acquisition_parallel(scene) -> numpy channel_buf",
                     "host_checksum": host_checksum},
-            "gpu_launches": args.steps, "kernel": "prt::k_acquire", "kernel_ms": k_ms,
+            "gpu_launches": acq["launches"], "kernel": "prt::k_acquire<%s>" % ("true" if n_tris else "false"),
+            "kernel_ms": launch_ms, "step_kernels_ms": k_ms,
             "wall_s_timed_region": wall,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "analytic scenes stage <= 8 KB of primitives in shared memory and the 12.8 MB accumulator "
-                                 "stays in L2: this configuration is instruction-issue bound, not HBM bound (see `issue`)"},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": ("mesh scene: rays x B_min(N) = %d B of node + triangle fetches (SURVEY 8(d)); the tree lives on "
+                                  "chip, the kernel is bound by traversal latency / SIMT divergence" % bvh_min_bytes(n_tris)) if n_tris else
+                                 ("analytic scenes stage <= 8 KB of primitives in shared memory and the 12.8 MB accumulator "
+                                  "stays in L2: this configuration is instruction-issue bound, not HBM bound (see `issue`)")},
             "clocks": clk,
         }
         # instruction-issue view (the binding limit for analytic scenes): ncu-measured warp instructions per
@@ -474,6 +533,18 @@ def main():
             line["cpu_baseline"] = {"value": rays_c / t_c / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
                                     "sample": f"{reps} x {C1_SPP * n_ae} paths (BASELINE config 1 path count) of the same scene, "
                                               f"oracle f32, {threads} threads, {t_c:.1f} s"}
+    else:
+        line = None
+    if not args.no_also:
+        # the other scene BASELINE.json's metric names (scenes/cbox.xml, config 4), measured briefly in the same job:
+        # wavefront path tracer, sample shards + one all-reduce of the film
+        del buf, flush
+        torch.cuda.empty_cache()
+        cb = pt_measure(args, "cbox", 3, 3, rank, world, device, 2, False)
+        if rank == 0:
+            line["also"] = {"cbox": {k: cb[k] for k in ("value", "unit", "ms_per_step", "msamples_per_s", "e2e", "gpu_launches",
+                                                         "kernel", "kernel_ms", "kernel_classes", "roofline", "config")}}
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -53,6 +53,18 @@ int prt_device_count(int *count);
 /* replaces mi.set_variant("cuda_ad_mono") (TestScene.py:3): binds a CUDA device */
 int prt_create(int device, prt_context **out);
 int prt_destroy(prt_context *);
+/* Per-kernel-class device timing for bench.py's roofline leg: between prt_profile_begin and prt_profile_read every
+ * kernel group the library enqueues is bracketed by a CUDA event pair ON THE STREAM IT IS LAUNCHED ON
+ * (`launches` counts kernels; the shading kernels of one bounce share one event pair).
+ * prt_profile_read waits for the recorded work, sums the elapsed times per class and switches profiling off. */
+enum { PRT_KC_GENERATE = 0, PRT_KC_TRACE_CLOSEST = 1, PRT_KC_TRACE_SHADOW = 2, PRT_KC_SHADE = 3, PRT_KC_FILM = 4,
+       PRT_KC_ACQUIRE = 5, PRT_KC_MEGAKERNEL = 6, PRT_KC_OTHER = 7, PRT_KC_COUNT = 8 };
+typedef struct {
+    double   ms[8];
+    uint32_t launches[8];
+} prt_kernel_times;
+int prt_profile_begin(prt_context *);
+int prt_profile_read(prt_context *, prt_kernel_times *out);
 int prt_device_info(prt_context *, int *sm_count, int *cc_major, int *cc_minor, uint64_t *global_mem_bytes);
 /* Page-locked host memory for result buffers.  prt_acquire / prt_render_path detect a pinned destination and
  * copy device -> host straight into it (per-angle slices overlapped with the kernel of the next angle);
@@ -166,6 +178,13 @@ int prt_render_path(prt_scene *, const prt_render_params *, uint64_t seed, uint3
 int prt_render_path_dev(prt_scene *, const prt_render_params *, uint64_t seed, uint32_t spp_total,
                         uint32_t sample_offset, uint32_t sample_stride, float *film_rgbw_dev, uint64_t *stats_dev,
                         void *stream);
+/* == mi.render(scene) as /root/reference/RayTracingV0.py:49 calls it: the film is developed ON THE DEVICE
+ * (hdrfilm: rgb = sum(w c) / sum(w), 0 where no sample landed) and only image_rgb [H][W][3] f32 crosses the
+ * bus.  A page-locked destination (prt_host_alloc) is written directly, without a staging copy. */
+int prt_render_image(prt_scene *, const prt_render_params *, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                     uint32_t sample_stride, float *image_rgb, prt_render_stats *stats /*nullable*/);
+/* develop a device-resident RGBW film (e.g. after the all-reduce over sample shards) into rgb_dev [n_pixels][3] */
+int prt_film_develop_dev(prt_context *, const float *film_rgbw_dev, uint64_t n_pixels, float *rgb_dev, void *stream);
 
 /* ---- "next" row f1: delay-and-sum beamformer + envelope (replaces ultraspy, USMain.py:129-208) -- */
 typedef struct {
@@ -179,6 +198,16 @@ int prt_das_beamform(prt_context *, const prt_das_params *, const float *channel
                      const double *angles_deg, const float *x, const float *z, float *rf, float *envelope);
 /* envelope of an already beamformed image rf [nx][nz] (DelayAndSum.compute_envelope, USMain.py:208) */
 int prt_envelope(prt_context *, const float *rf, int32_t nx, int32_t nz, float *envelope);
+
+
+/* ---- "next" row f4: pulse shaping (prototype at /root/reference/RayTracingV0.py:185-204, "UltraRay Eq. 14").
+ * channel [n_rows][T] of delta echoes -> out [n_rows][T] = zero-phase convolution of every row with
+ * h(t) = sin(2 pi fc t) exp(-t^2 / sigma_s^2), truncated at |t| <= 4 sigma_s (<= 1024 samples either side).
+ * UltraIntegrator's `wave_cycles` (CustomIntegrator.py:20, unused there) maps to sigma_s = wave_cycles / (4 fc). */
+int prt_pulse_shape(prt_context *, const float *channel, uint64_t n_rows, int32_t time_samples, double fs, double fc,
+                    double sigma_s, float *out);
+int prt_pulse_shape_dev(prt_context *, const float *channel_dev, uint64_t n_rows, int32_t time_samples, double fs, double fc,
+                        double sigma_s, float *out_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -230,3 +230,19 @@ def shapes_from_desc(desc):
         m = desc.materials[s.material]
         out.append(Shape(s.kind, s.to_world, m.params[0], m.params[1]))
     return out
+
+
+def pulse_shape(channel, fs, fc, sigma_s, cut=4.0):
+    """Oracle for the "next" row f4 (pulse shaping): the prototype's echo model, /root/reference/RayTracingV0.py:185-204
+    (`pulse(t, t0, amp, fc, sigma) = amp * sin(2 pi fc (t - t0)) * exp(-((t - t0)^2) / sigma^2)`, summed per echo),
+    for echoes that sit on the sample grid: out[i] = sum_j in[j] h((i - j) / fs).  float64, truncated at |t| <= cut * sigma
+    like the kernel (exp(-16) = 1.1e-7).  Test infrastructure only."""
+    ch = np.asarray(channel, dtype=np.float64)
+    half = int(math.ceil(cut * sigma_s * fs))
+    n = np.arange(-half, half + 1, dtype=np.float64)
+    h = np.sin(2.0 * np.pi * fc * n / fs) * np.exp(-((n / fs) ** 2) / sigma_s ** 2)
+    flat = ch.reshape(-1, ch.shape[-1])
+    out = np.empty_like(flat)
+    for r in range(flat.shape[0]):
+        out[r] = np.convolve(flat[r], h, mode="full")[half:half + flat.shape[1]]
+    return out.reshape(ch.shape)

@@ -25,11 +25,11 @@ QF_CONNECT_TO_TARGET = 1 << 4
 
 # every symbol include/prt_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "prt_last_error", "prt_version", "prt_device_count", "prt_create", "prt_destroy", "prt_device_info", "prt_host_alloc", "prt_host_free",
+    "prt_last_error", "prt_version", "prt_device_count", "prt_create", "prt_destroy", "prt_device_info", "prt_profile_begin", "prt_profile_read", "prt_host_alloc", "prt_host_free",
     "prt_scene_create", "prt_scene_destroy", "prt_scene_add_material", "prt_scene_set_material_param",
     "prt_scene_add_primitive", "prt_scene_add_mesh", "prt_scene_commit", "prt_trace_closest", "prt_trace_occluded",
     "prt_ultra_bsdf_sample", "prt_acquire", "prt_acquire_dev", "prt_acquire_trace", "prt_render_path",
-    "prt_render_path_dev", "prt_das_beamform", "prt_envelope",
+    "prt_render_path_dev", "prt_render_image", "prt_film_develop_dev", "prt_das_beamform", "prt_envelope", "prt_pulse_shape", "prt_pulse_shape_dev",
 ]
 
 
@@ -66,6 +66,16 @@ class BvhStatsC(C.Structure):
                     max_leaf_size=self.max_leaf_size, build_ms=self.build_ms, sah_cost=self.sah_cost,
                     scene_lo=list(self.scene_lo), scene_hi=list(self.scene_hi), device_bytes=self.device_bytes,
                     n_nodes8=self.n_nodes8, bvh8_levels=self.bvh8_levels, bvh8_build_ms=self.bvh8_build_ms)
+
+
+KERNEL_CLASSES = ("generate", "trace_closest", "trace_shadow", "shade", "film", "acquire", "megakernel", "other")
+
+
+class KernelTimesC(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint32 * 8)]
+
+    def as_dict(self):
+        return {n: {"ms": self.ms[i], "launches": int(self.launches[i])} for i, n in enumerate(KERNEL_CLASSES) if self.launches[i]}
 
 
 class RenderParamsC(C.Structure):
@@ -112,6 +122,8 @@ def load():
     L.prt_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.prt_destroy.argtypes = [vp]
     L.prt_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), u64p]
+    L.prt_profile_begin.argtypes = [vp]
+    L.prt_profile_read.argtypes = [vp, C.POINTER(KernelTimesC)]
     L.prt_host_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     L.prt_host_free.argtypes = [vp, vp]
     L.prt_scene_create.argtypes = [vp, C.POINTER(vp)]
@@ -131,8 +143,12 @@ def load():
     L.prt_render_path.argtypes = [vp, C.POINTER(RenderParamsC), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, fp,
                                   C.POINTER(RenderStatsC)]
     L.prt_render_path_dev.argtypes = [vp, C.POINTER(RenderParamsC), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
+    L.prt_render_image.argtypes = L.prt_render_path.argtypes
+    L.prt_film_develop_dev.argtypes = [vp, vp, C.c_uint64, vp, vp]
     L.prt_das_beamform.argtypes = [vp, C.POINTER(DasParamsC), fp, fp, dp, fp, fp, fp, fp]
     L.prt_envelope.argtypes = [vp, fp, C.c_int32, C.c_int32, fp]
+    L.prt_pulse_shape.argtypes = [vp, fp, C.c_uint64, C.c_int32, C.c_double, C.c_double, C.c_double, fp]
+    L.prt_pulse_shape_dev.argtypes = [vp, vp, C.c_uint64, C.c_int32, C.c_double, C.c_double, C.c_double, vp, vp]
     _lib = L
     return L
 

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "prt_hit.cuh"
 #include "prt_internal.h"
 
 namespace prt {
@@ -282,8 +283,11 @@ static int launch_acquire(prt_context *c, const AcqDev &P, cudaStream_t st) {
     uint64_t grid = (uint64_t) c->sm_count * per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    if (tris) k_acquire<true><<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
-    else k_acquire<false><<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
+    {
+        ProfScope ps(c, PRT_KC_ACQUIRE, st);
+        if (tris) k_acquire<true><<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
+        else k_acquire<false><<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
+    }
     PRT_CUDA(cudaGetLastError());
     return PRT_OK;
 }

@@ -88,9 +88,89 @@ __global__ void __launch_bounds__(256) k_envelope(const float *__restrict__ rf, 
     }
 }
 
+// "next" row f4: pulse shaping.  The acquisition deposits delta echoes (one sample per arrival);
+// the authors' prototype (/root/reference/RayTracingV0.py:185-204, "UltraRay Eq. 14") turns them into band-limited RF
+// by summing amp * sin(2 pi fc (t - t0)) * exp(-(t - t0)^2 / sigma^2) per echo.  With echoes binned on the sample
+// grid that is a zero-phase FIR along each channel row:
+//     out[i] = sum_j in[j] h((i - j) / fs),   h(t) = sin(2 pi fc t) exp(-t^2 / sigma^2),   |t| <= PULSE_CUT sigma
+// One CTA shapes a tile of 1024 samples of one row: row tile + halo and the taps live in shared memory, so every
+// input sample is read from HBM once (+ halo) and every output written once.
+static constexpr int PULSE_TILE = 1024;
+static constexpr int PULSE_MAX_HALF = 1024;     // max taps on either side of the centre
+static constexpr float PULSE_CUT = 4.0f;        // exp(-16) = 1.1e-7: below f32 resolution of the centre taps
+
+__global__ void __launch_bounds__(256) k_pulse_shape(const float *__restrict__ in, float *__restrict__ out, int T, int half,
+                                                     float w_cyc /* 2 fc / fs */, float inv_sig /* 1 / (sigma fs) */) {
+    extern __shared__ float sm[];
+    float *taps = sm;                      // [2 half + 1]
+    float *tile = sm + 2 * half + 1;       // [PULSE_TILE + 2 half]
+    const size_t row = blockIdx.y;
+    const int i0 = blockIdx.x * PULSE_TILE;
+    for (int k = threadIdx.x; k <= 2 * half; k += blockDim.x) {
+        const float n = (float) (k - half), u = n * inv_sig;
+        taps[k] = sinpif(w_cyc * n) * expf(-u * u);
+    }
+    for (int k = threadIdx.x; k < PULSE_TILE + 2 * half; k += blockDim.x) {
+        const int j = i0 - half + k;
+        tile[k] = (j >= 0 && j < T) ? __ldg(in + row * (size_t) T + j) : 0.0f;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < PULSE_TILE; k += blockDim.x) {
+        const int i = i0 + k;
+        if (i >= T) break;
+        float acc = 0.0f;
+        // out[i] = sum_m in[i - m] h(m), m = -half..half; tile index of in[i - m] is (i - m) - (i0 - half) = k + half - m
+        for (int m = -half; m <= half; m++) acc = fmaf(tile[k + half - m], taps[m + half], acc);
+        out[row * (size_t) T + i] = acc;
+    }
+}
+
+static int launch_pulse(const float *in_d, float *out_d, uint64_t n_rows, int T, double fs, double fc, double sigma, cudaStream_t st) {
+    PRT_REQUIRE(fs > 0 && fc > 0 && sigma > 0 && T > 0, "prt_pulse_shape: invalid parameters");
+    const int half = (int) std::ceil(PULSE_CUT * sigma * fs);
+    PRT_REQUIRE(half <= PULSE_MAX_HALF, "prt_pulse_shape: pulse longer than 2049 samples");
+    PRT_REQUIRE(n_rows < 65536, "prt_pulse_shape: too many rows");
+    const size_t smem = sizeof(float) * ((size_t) 2 * half + 1 + PULSE_TILE + 2 * half);
+    if (smem > 48 * 1024) PRT_CUDA(cudaFuncSetAttribute(k_pulse_shape, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    dim3 grid((T + PULSE_TILE - 1) / PULSE_TILE, (unsigned) n_rows);
+    k_pulse_shape<<<grid, 256, smem, st>>>(in_d, out_d, T, half, (float) (2.0 * fc / fs), (float) (1.0 / (sigma * fs)));
+    PRT_CUDA(cudaGetLastError());
+    return PRT_OK;
+}
+
 }  // namespace prt
 
 using namespace prt;
+
+extern "C" int prt_pulse_shape_dev(prt_context *c, const float *channel_dev, uint64_t n_rows, int32_t time_samples, double fs,
+                                   double fc, double sigma_s, float *out_dev, void *stream) {
+    PRT_REQUIRE(c && channel_dev && out_dev && channel_dev != out_dev, "prt_pulse_shape_dev: null or aliased argument");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    PRT_CUDA(cudaSetDevice(c->device));
+    return launch_pulse(channel_dev, out_dev, n_rows, time_samples, fs, fc, sigma_s, (cudaStream_t) stream);
+}
+
+extern "C" int prt_pulse_shape(prt_context *c, const float *channel, uint64_t n_rows, int32_t time_samples, double fs, double fc,
+                               double sigma_s, float *out) {
+    PRT_REQUIRE(c && channel && out && n_rows > 0 && time_samples > 0, "prt_pulse_shape: invalid argument");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    PRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t n = (size_t) n_rows * (size_t) time_samples;
+    float *in_d = nullptr, *out_d = nullptr;
+    cudaError_t e = cudaMalloc(&in_d, sizeof(float) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&out_d, sizeof(float) * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(in_d, channel, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+    int rc = PRT_OK;
+    if (e == cudaSuccess) rc = launch_pulse(in_d, out_d, n_rows, time_samples, fs, fc, sigma_s, st);
+    if (e == cudaSuccess && rc == PRT_OK) e = cudaMemcpyAsync(out, out_d, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == PRT_OK) e = cudaStreamSynchronize(st);
+    cudaFree(in_d);
+    cudaFree(out_d);
+    if (rc) return rc;
+    PRT_CUDA(e);
+    return PRT_OK;
+}
 
 extern "C" int prt_das_beamform(prt_context *c, const prt_das_params *p, const float *channel, const float *tx_delays,
                                 const double *angles_deg, const float *x, const float *z, float *rf, float *envelope) {

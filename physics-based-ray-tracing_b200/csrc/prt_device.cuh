@@ -444,43 +444,6 @@ __device__ __forceinline__ void fill_tri_hit(const DScene &sc, int sorted_tri, f
     finish_frame(h, du);
 }
 
-// scene.ray_intersect: nearest hit over analytic primitives (staged in shared memory by the caller)
-// and the triangle BVH
-// TRIS = false compiles the BVH traversal (and its stack) out: kernels specialised for analytic-only scenes
-template <bool TRIS = true>
-__device__ __forceinline__ bool closest_hit(const DScene &sc, const DPrim *prims, float3 o, float3 d, float tmax, Hit &h) {
-    int best = -1;
-    float tb = tmax;
-    for (int i = 0; i < sc.n_prims; i++) {
-        float t = intersect_prim(prims[i], o, d, tb);
-        if (t >= 0.0f && (best < 0 || t < tb)) {
-            best = i;
-            tb = t;
-        }
-    }
-    if (TRIS) {
-        float b1 = 0.0f, b2 = 0.0f;
-        float tt = tb;
-        int tri = traverse_bvh<false>(sc, o, d, tt, b1, b2);
-        if (tri >= 0 && (best < 0 || tt < tb)) {
-            fill_tri_hit(sc, tri, tt, b1, b2, h);
-            return true;
-        }
-    }
-    if (best < 0) return false;
-    fill_prim_hit(prims[best], best, o, d, tb, h);
-    return true;
-}
-
-template <bool TRIS = true>
-__device__ __forceinline__ bool occluded(const DScene &sc, const DPrim *prims, float3 o, float3 d, float tmax) {
-    bool hit = false;
-    for (int i = 0; i < sc.n_prims; i++) hit |= intersect_prim(prims[i], o, d, tmax) >= 0.0f;
-    if (hit || !TRIS) return hit;
-    float b1, b2, tt = tmax;
-    return traverse_bvh<true>(sc, o, d, tt, b1, b2) >= 0;
-}
-
 // si.spawn_ray(d) origin
 __device__ __forceinline__ float3 spawn_origin(float3 p, float3 ng, float3 d) {
     float m = fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z)));

@@ -54,7 +54,29 @@ struct prt_context {
     void     *pinned;    size_t pinned_cap;   // pinned staging for D2H of results
     void     *wf_dev = nullptr; size_t wf_cap = 0;   // wavefront path-tracer state / queues (prt_wavefront.cu)
     int       last_launches = 0;              // kernels enqueued by the most recent render call
+    // optional per-kernel-class timing (prt_profile_begin / prt_profile_read): CUDA event pairs on the launching stream
+    bool prof_on = false;
+    struct ProfPair { int cls, kernels; cudaEvent_t e0, e1; };
+    std::vector<ProfPair> prof;
 };
+
+namespace prt {
+// brackets the launches of one kernel class with an event pair while profiling is on (bench.py's roofline leg);
+// a no-op otherwise
+struct ProfScope {
+    prt_context *c; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr; int cls, kernels = 1;
+    ProfScope(prt_context *c_, int cls_, cudaStream_t st_) : c(c_), st(st_), cls(cls_) {
+        if (!c->prof_on) return;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
+        cudaEventRecord(e0, st);
+    }
+    ~ProfScope() {
+        if (!e0) return;
+        cudaEventRecord(e1, st);
+        c->prof.push_back({cls, kernels, e0, e1});
+    }
+};
+}  // namespace prt
 
 struct prt_scene {
     prt_context *ctx;

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdlib>
 
+#include "prt_hit.cuh"
 #include "prt_internal.h"
 #include "prt_path.h"
 
@@ -93,6 +94,27 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_render_path(const PtDev P) {
     }
 }
 
+// hdrfilm develop (scenes/cbox.xml:25-31): rgb = sum(w c) / sum(w); pixels no sample reached stay 0
+__global__ void __launch_bounds__(256) k_film_develop(const float4 *__restrict__ film, uint64_t n_pixels, float *__restrict__ rgb) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_pixels; i += (uint64_t) gridDim.x * blockDim.x) {
+        const float4 f = film[i];
+        const float inv = f.w > 0.0f ? 1.0f / fmaxf(f.w, 1e-30f) : 0.0f;
+        rgb[3 * i + 0] = f.x * inv;
+        rgb[3 * i + 1] = f.y * inv;
+        rgb[3 * i + 2] = f.z * inv;
+    }
+}
+
+static int launch_develop(prt_context *c, const float *film, uint64_t n_pixels, float *rgb, cudaStream_t st) {
+    uint64_t grid = (n_pixels + 255) / 256;
+    const uint64_t cap = (uint64_t) c->sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    k_film_develop<<<(unsigned) grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(film), n_pixels, rgb);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_OK;
+}
+
 static int fill_pt(prt_scene *s, const prt_render_params *p, uint64_t seed, uint32_t spp_total, uint32_t s_offset, uint32_t s_stride,
                    PtDev &P) {
     PRT_REQUIRE(p->width > 0 && p->height > 0 && p->max_depth >= 0 && spp_total > 0, "render_path: invalid render parameters");
@@ -144,7 +166,10 @@ static int launch_pt(prt_context *c, const PtDev &P, cudaStream_t st) {
     int grid = c->sm_count * per_sm;
     int n_tiles = P.tiles_x * P.tiles_y;
     if (grid > n_tiles) grid = n_tiles;
-    k_render_path<<<grid, PT_THREADS, 0, st>>>(P);
+    {
+        ProfScope ps(c, PRT_KC_MEGAKERNEL, st);
+        k_render_path<<<grid, PT_THREADS, 0, st>>>(P);
+    }
     PRT_CUDA(cudaGetLastError());
     c->last_launches = 1;
     return PRT_OK;
@@ -170,8 +195,16 @@ int prt_render_path_dev(prt_scene *s, const prt_render_params *p, uint64_t seed,
     return launch_pt(s->ctx, P, (cudaStream_t) stream);
 }
 
-int prt_render_path(prt_scene *s, const prt_render_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
-                    uint32_t sample_stride, float *film_rgbw, prt_render_stats *stats) {
+int prt_film_develop_dev(prt_context *c, const float *film_rgbw_dev, uint64_t n_pixels, float *rgb_dev, void *stream) {
+    PRT_REQUIRE(c && film_rgbw_dev && rgb_dev, "prt_film_develop_dev: null argument");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    PRT_CUDA(cudaSetDevice(c->device));
+    return launch_develop(c, film_rgbw_dev, n_pixels, rgb_dev, (cudaStream_t) stream);
+}
+
+// host-buffer render: develop = false -> out is the RGBW film [H][W][4]; true -> the developed image [H][W][3]
+static int render_host(prt_scene *s, const prt_render_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                       uint32_t sample_stride, float *film_rgbw, prt_render_stats *stats, bool develop) {
     PRT_REQUIRE(s && p && film_rgbw, "prt_render_path: null argument");
     if (!s->committed) { set_error("prt_render_path: scene not committed"); return PRT_ERR_STATE; }
     std::lock_guard<std::mutex> lk(s->ctx->mtx);
@@ -182,7 +215,8 @@ int prt_render_path(prt_scene *s, const prt_render_params *p, uint64_t seed, uin
     int rc = fill_pt(s, p, seed, spp_total, sample_offset, sample_stride, P);
     if (rc) return rc;
     const size_t n = (size_t) p->width * p->height * 4;
-    rc = ensure_scratch(c, n, 0, 0);
+    const size_t n_out = develop ? n / 4 * 3 : n;
+    rc = ensure_scratch(c, n, develop ? n_out : 0, 0);
     if (rc) return rc;
     cudaEvent_t e0, e1, e2, e3;
     PRT_CUDA(cudaEventCreate(&e0)); PRT_CUDA(cudaEventCreate(&e1)); PRT_CUDA(cudaEventCreate(&e2)); PRT_CUDA(cudaEventCreate(&e3));
@@ -194,18 +228,25 @@ int prt_render_path(prt_scene *s, const prt_render_params *p, uint64_t seed, uin
     PRT_CUDA(cudaEventRecord(e1, st));
     rc = launch_pt(c, P, st);
     if (rc) return rc;
+    const float *src = c->acc_dev;
+    if (develop) {
+        rc = launch_develop(c, c->acc_dev, n / 4, c->aux_dev, st);
+        if (rc) return rc;
+        c->last_launches++;
+        src = c->aux_dev;
+    }
     PRT_CUDA(cudaEventRecord(e2, st));
     float *pin = reinterpret_cast<float *>(c->pinned);
     cudaPointerAttributes attr;
     const bool pinned_dst = cudaPointerGetAttributes(&attr, film_rgbw) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (pinned_dst) pin = film_rgbw;
-    PRT_CUDA(cudaMemcpyAsync(pin, c->acc_dev, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    PRT_CUDA(cudaMemcpyAsync(pin, src, sizeof(float) * n_out, cudaMemcpyDeviceToHost, st));
     uint64_t hs[8];
     PRT_CUDA(cudaMemcpyAsync(hs, c->stats_dev, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
     PRT_CUDA(cudaEventRecord(e3, st));
     PRT_CUDA(cudaStreamSynchronize(st));
-    if (!pinned_dst) memcpy(film_rgbw, pin, sizeof(float) * n);
+    if (!pinned_dst) memcpy(film_rgbw, pin, sizeof(float) * n_out);
     if (stats) {
         stats->paths = hs[0]; stats->segments = hs[1]; stats->rays = hs[2]; stats->shadow_rays = hs[3];
         PRT_CUDA(cudaEventElapsedTime(&stats->kernel_ms, e1, e2));
@@ -215,6 +256,16 @@ int prt_render_path(prt_scene *s, const prt_render_params *p, uint64_t seed, uin
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     return PRT_OK;
+}
+
+int prt_render_path(prt_scene *s, const prt_render_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                    uint32_t sample_stride, float *film_rgbw, prt_render_stats *stats) {
+    return render_host(s, p, seed, spp_total, sample_offset, sample_stride, film_rgbw, stats, false);
+}
+
+int prt_render_image(prt_scene *s, const prt_render_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                     uint32_t sample_stride, float *image_rgb, prt_render_stats *stats) {
+    return render_host(s, p, seed, spp_total, sample_offset, sample_stride, image_rgb, stats, true);
 }
 
 }  // extern "C"

@@ -1,6 +1,7 @@
 // prt_query.cu -- batched ray queries at the scene.ray_intersect boundary
 // (/root/reference/CustomIntegrator.py:146,159,309,324) and batched UltraBSDF.sample
 // (/root/reference/CustomBSDF.py:87-175).  These are the entry points the parity tests drive.
+#include "prt_hit.cuh"
 #include "prt_internal.h"
 
 namespace prt {

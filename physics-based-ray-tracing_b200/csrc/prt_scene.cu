@@ -152,12 +152,43 @@ int prt_destroy(prt_context *c) {
     if (c->stats_dev) cudaFree(c->stats_dev);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->wf_dev) cudaFree(c->wf_dev);
+    for (auto &pp : c->prof) { cudaEventDestroy(pp.e0); cudaEventDestroy(pp.e1); }
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->slice_done[0]);
     cudaEventDestroy(c->slice_done[1]);
     delete c;
     return PRT_OK;
+}
+
+int prt_profile_begin(prt_context *c) {
+    PRT_REQUIRE(c, "prt_profile_begin: null context");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    for (auto &pp : c->prof) { cudaEventDestroy(pp.e0); cudaEventDestroy(pp.e1); }
+    c->prof.clear();
+    c->prof_on = true;
+    return PRT_OK;
+}
+
+int prt_profile_read(prt_context *c, prt_kernel_times *out) {
+    PRT_REQUIRE(c && out, "prt_profile_read: null argument");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    PRT_CUDA(cudaSetDevice(c->device));
+    for (int k = 0; k < PRT_KC_COUNT; k++) { out->ms[k] = 0.0; out->launches[k] = 0; }
+    int rc = PRT_OK;
+    for (auto &pp : c->prof) {
+        float ms = 0.0f;
+        cudaError_t e = cudaEventSynchronize(pp.e1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, pp.e0, pp.e1);
+        if (e != cudaSuccess && rc == PRT_OK) rc = cuda_fail(e, "prt_profile_read", __FILE__, __LINE__);
+        out->ms[pp.cls] += ms;
+        out->launches[pp.cls] += (uint32_t) pp.kernels;
+        cudaEventDestroy(pp.e0);
+        cudaEventDestroy(pp.e1);
+    }
+    c->prof.clear();
+    c->prof_on = false;
+    return rc;
 }
 
 int prt_device_info(prt_context *c, int *sm_count, int *cc_major, int *cc_minor, uint64_t *global_mem_bytes) {

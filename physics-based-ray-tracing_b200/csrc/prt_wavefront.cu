@@ -529,24 +529,39 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
         B.j0 = (uint32_t) j0;
         B.n_layers = (uint32_t) (P.n_s - j0 < layers ? P.n_s - j0 : layers);
         PRT_CUDA(cudaMemsetAsync(B.cnt, 0, cnt_bytes, st));
-        k_wf_generate<<<g_gen, WF_SHADE_THREADS, 0, st>>>(P, B);
-        launches++;
-        for (int b = 0; b < bounces; b++) {
-            k_wf_trace<false><<<g_ext, WF_TRACE_THREADS, 0, st>>>(P, B, b);
+        {
+            ProfScope ps(c, PRT_KC_GENERATE, st);
+            k_wf_generate<<<g_gen, WF_SHADE_THREADS, 0, st>>>(P, B);
             launches++;
-            if (P.kind_mask & (1u << PRT_MAT_DIFFUSE)) { k_wf_shade<0><<<g_shade[0], WF_SHADE_THREADS, 0, st>>>(P, B, b); launches++; }
-            if (P.kind_mask & (1u << PRT_MAT_DIELECTRIC)) { k_wf_shade<1><<<g_shade[1], WF_SHADE_THREADS, 0, st>>>(P, B, b); launches++; }
-            if (P.kind_mask & ~((1u << PRT_MAT_DIFFUSE) | (1u << PRT_MAT_DIELECTRIC))) {
-                k_wf_shade<2><<<g_shade[2], WF_SHADE_THREADS, 0, st>>>(P, B, b);
+        }
+        for (int b = 0; b < bounces; b++) {
+            {
+                ProfScope ps(c, PRT_KC_TRACE_CLOSEST, st);
+                k_wf_trace<false><<<g_ext, WF_TRACE_THREADS, 0, st>>>(P, B, b);
                 launches++;
             }
+            {
+                ProfScope ps(c, PRT_KC_SHADE, st);
+                const int before = launches;
+                if (P.kind_mask & (1u << PRT_MAT_DIFFUSE)) { k_wf_shade<0><<<g_shade[0], WF_SHADE_THREADS, 0, st>>>(P, B, b); launches++; }
+                if (P.kind_mask & (1u << PRT_MAT_DIELECTRIC)) { k_wf_shade<1><<<g_shade[1], WF_SHADE_THREADS, 0, st>>>(P, B, b); launches++; }
+                if (P.kind_mask & ~((1u << PRT_MAT_DIFFUSE) | (1u << PRT_MAT_DIELECTRIC))) {
+                    k_wf_shade<2><<<g_shade[2], WF_SHADE_THREADS, 0, st>>>(P, B, b);
+                    launches++;
+                }
+                ps.kernels = launches - before;
+            }
             if (b + 1 < P.max_depth && (P.kind_mask & (1u << PRT_MAT_DIFFUSE)) && P.sc.n_emitters > 0) {
+                ProfScope ps(c, PRT_KC_TRACE_SHADOW, st);
                 k_wf_trace<true><<<g_sh, WF_TRACE_THREADS, 0, st>>>(P, B, b);
                 launches++;
             }
         }
-        k_wf_film<<<n_tiles, 256, 0, st>>>(P, B);
-        launches++;
+        {
+            ProfScope ps(c, PRT_KC_FILM, st);
+            k_wf_film<<<n_tiles, 256, 0, st>>>(P, B);
+            launches++;
+        }
         PRT_CUDA(cudaGetLastError());
     }
     c->last_launches = launches;

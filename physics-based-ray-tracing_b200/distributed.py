@@ -68,7 +68,9 @@ def acquire_sharded(dev_scene, params, seed: int, spp_total: int, to_host: bool 
     return hb, htx, st
 
 
-def render_sharded(dev_scene, rp, seed: int, spp_total: int, to_host: bool = True, film=None, stats=None):
+def render_sharded(dev_scene, rp, seed: int, spp_total: int, to_host: bool = True, film=None, stats=None, develop: bool = False):
+    """Rank-local sample shard of a render + ONE all-reduce of the RGBW film.  ``develop``: divide by the weight
+    channel on the device AFTER the reduce (so sharded == unsharded up to summation order) and return [H,W,3]."""
     import torch
     dist, rank, world = _dist()
     device = torch.device("cuda", dev_scene.ctx.device)
@@ -88,6 +90,10 @@ def render_sharded(dev_scene, rp, seed: int, spp_total: int, to_host: bool = Tru
         if world > 1:
             dist.all_reduce(film, op=dist.ReduceOp.SUM)
             dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        if develop:
+            rgb = torch.empty((rp.height, rp.width, 3), dtype=torch.float32, device=device)
+            dev_scene.develop_dev(film.data_ptr(), rp.height * rp.width, rgb.data_ptr(), stream.cuda_stream)
+            film = rgb
         if not to_host:
             return film, stats
         hf, hs = film.cpu().numpy(), stats.cpu().numpy()

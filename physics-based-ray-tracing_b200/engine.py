@@ -35,6 +35,15 @@ class Context:
         check(self.L.prt_device_info(h, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem)))
         self.sm_count, self.cc, self.global_mem = sm.value, (maj.value, mnr.value), mem.value
 
+    def profile_begin(self):
+        """Start per-kernel-class event timing inside the library (bench.py's roofline leg)."""
+        check(self.L.prt_profile_begin(self.h), "prt_profile_begin")
+
+    def profile_read(self) -> dict:
+        kt = capi.KernelTimesC()
+        check(self.L.prt_profile_read(self.h, C.byref(kt)), "prt_profile_read")
+        return kt.as_dict()
+
     def pinned_array(self, shape, dtype=np.float32) -> np.ndarray:
         """A page-locked numpy array (prt_host_alloc) for a result: D2H goes straight into it -- no staging memcpy,
         no page faults on a fresh allocation.  Buffers are pooled per shape and a buffer is handed out again only
@@ -181,6 +190,18 @@ class DeviceScene:
               "prt_render_path")
         return film, st.as_dict()
 
+    def render_image(self, rp: "capi.RenderParamsC", seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1):
+        """mi.render(scene): the film is developed on the device; returns (image [H,W,3] f32 in page-locked memory, stats)."""
+        img = self.ctx.pinned_array((rp.height, rp.width, 3), np.float32)
+        st = capi.RenderStatsC()
+        check(self.L.prt_render_image(self.h, C.byref(rp), seed, spp, sample_offset, sample_stride, fptr(img), C.byref(st)),
+              "prt_render_image")
+        return img, st.as_dict()
+
+    def develop_dev(self, film_ptr: int, n_pixels: int, rgb_ptr: int, stream: int = 0):
+        check(self.L.prt_film_develop_dev(self.ctx.h, C.c_void_p(film_ptr), n_pixels, C.c_void_p(rgb_ptr), C.c_void_p(stream or None)),
+              "prt_film_develop_dev")
+
     def render_path_dev(self, rp: "capi.RenderParamsC", film_ptr: int, stats_ptr: int = 0, stream: int = 0, seed: int = 0,
                         spp: int = 1, sample_offset: int = 0, sample_stride: int = 1):
         check(self.L.prt_render_path_dev(self.h, C.byref(rp), seed, spp, sample_offset, sample_stride, C.c_void_p(film_ptr),
@@ -234,3 +255,19 @@ def envelope(rf, context: Optional[Context] = None):
     env = np.empty_like(r)
     check(ctx.L.prt_envelope(ctx.h, fptr(r), r.shape[0], r.shape[1], fptr(env)), "prt_envelope")
     return env
+
+
+def pulse_shape(channel, fs, fc, sigma_s=None, wave_cycles=None, context: Optional[Context] = None):
+    """Band-limit delta echoes with the Gaussian-modulated tone burst of /root/reference/RayTracingV0.py:185-204 on the
+    GPU.  channel [..., T] f32 -> same shape.  ``sigma_s`` (seconds) or ``wave_cycles`` (sigma = cycles / (4 fc))."""
+    ctx = context or Context.get()
+    if sigma_s is None:
+        if wave_cycles is None:
+            raise ValueError("pulse_shape: give sigma_s or wave_cycles")
+        sigma_s = float(wave_cycles) / (4.0 * float(fc))
+    ch = np.ascontiguousarray(channel, dtype=np.float32)
+    T = ch.shape[-1]
+    rows = ch.size // T
+    out = np.empty_like(ch)
+    check(ctx.L.prt_pulse_shape(ctx.h, fptr(ch), rows, T, float(fs), float(fc), float(sigma_s), fptr(out)), "prt_pulse_shape")
+    return out

@@ -57,6 +57,9 @@ class UltraIntegrator(mi.SamplingIntegrator):
         self.seed = int(props.get('seed', 0))
         self.quirk_flags = int(props.get('quirk_flags', 0))
         self.max_path_len = float(props.get('max_path_len', 0.2))       # hard-coded 0.2 in the reference (:141)
+        # pulse shaping: convolve the delta echoes with a `wave_cycles`-long Gaussian-modulated tone
+        # burst (the prototype's model, RayTracingV0.py:185-204).  Off by default: the reference never uses wave_cycles.
+        self.shape_pulse = bool(props.get('shape_pulse', False))
         self.last_stats = None
 
     # :52-53 -- the Mitsuba entry point is a stub in the reference
@@ -93,6 +96,9 @@ class UltraIntegrator(mi.SamplingIntegrator):
             buf, tx, st = acquire_sharded(dev, p, seed=self.seed, spp_total=spp, to_host=True)
         self.last_stats = st
         self.ray_count += int(st["segments"])
+        if self.shape_pulse:
+            from prt_b200.engine import pulse_shape
+            buf = pulse_shape(buf, self.fs, self.frequency, wave_cycles=self.wave_cycles, context=dev.ctx)
         return buf, tx
 
     def simulate_acquisition(self, scene):
@@ -176,13 +182,12 @@ class PathIntegrator(mi.SamplingIntegrator):
         except ImportError:
             pass
         if world == 1:
-            film, st = dev.render_path(rp, seed=seed, spp=spp)
+            img, st = dev.render_image(rp, seed=seed, spp=spp)
         else:
             from prt_b200.distributed import render_sharded
-            film, st = render_sharded(dev, rp, seed=seed, spp_total=spp, to_host=True)
+            img, st = render_sharded(dev, rp, seed=seed, spp_total=spp, to_host=True, develop=True)
         self.last_stats = st
-        w = film[..., 3:4]
-        return np.where(w > 0, film[..., :3] / np.maximum(w, 1e-30), 0.0).astype(np.float32)
+        return img
 
     def sample(self, scene, sampler, ray, medium, active=True):
         raise NotImplementedError("per-ray sample() is not exposed; use render()")

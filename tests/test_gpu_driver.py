@@ -57,6 +57,41 @@ def test_das_matches_numpy():
     assert np.abs(envelope(rf) - env).max() <= 1e-6 * ref_env.max()
 
 
+def test_pulse_shape_matches_oracle():
+    """Row f4: delta echoes -> Gaussian-modulated tone bursts (RayTracingV0.py:185-204) against the float64 numpy oracle;
+    ragged sizes (T not a multiple of the 1024-sample tile, echoes at both row ends), one-echo analytic check."""
+    import pyref
+    from prt_b200.engine import pulse_shape
+    rng = np.random.default_rng(3)
+    fs, fc = 50e6, 3e6
+    for (rows, T, cycles) in [((3, 5), 2500, 5), ((1,), 1024, 2), ((2,), 37, 1), ((4,), 10000, 8)]:
+        ch = np.zeros(rows + (T,), dtype=np.float32)
+        k = max(T // 40, 3)
+        flat = ch.reshape(-1, T)
+        for r in range(flat.shape[0]):
+            idx = rng.integers(0, T, size=k)
+            flat[r, idx] = rng.normal(size=k).astype(np.float32)
+            flat[r, 0], flat[r, T - 1] = 1.0, -0.5            # echoes on both edges: the halo is zero-padded
+        sigma = cycles / (4 * fc)
+        got = pulse_shape(ch, fs, fc, wave_cycles=cycles)
+        ref = pyref.pulse_shape(ch, fs, fc, sigma)
+        assert got.shape == ch.shape and got.dtype == np.float32
+        assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1.0), (rows, T, cycles)
+    # a single unit echo at sample 500 reproduces the prototype's pulse() sampled on the grid
+    ch = np.zeros((1, 1000), dtype=np.float32)
+    ch[0, 500] = 2.0
+    t = (np.arange(1000) - 500) / fs
+    sigma = 1e-7
+    expect = 2.0 * np.sin(2 * np.pi * fc * t) * np.exp(-t ** 2 / sigma ** 2)
+    expect[np.abs(t) > 4 * sigma + 0.5 / fs] = 0.0
+    assert np.abs(pulse_shape(ch, fs, fc, sigma_s=sigma)[0] - expect).max() < 1e-5
+    # linearity: shaping is a linear map of the channel data
+    a, b = rng.normal(size=(2, 3, 700)).astype(np.float32)
+    lhs = pulse_shape(a + 2 * b, fs, fc, wave_cycles=3)
+    rhs = pulse_shape(a, fs, fc, wave_cycles=3) + 2 * pulse_shape(b, fs, fc, wave_cycles=3)
+    assert np.abs(lhs - rhs).max() <= 1e-4 * np.abs(lhs).max()
+
+
 def test_usmain_call_sequence():
     """What USMain.py does, with 2 optimisation iterations instead of 25 and 64 samples per element so that the
     finite-difference loss is not pure noise."""

@@ -81,6 +81,12 @@ def test_render_api_through_plugins():
     # red wall is on the +x side = image right (camera looks down -z with +x to its left... see sensor frame)
     left, right = img[10:22, 1:4].mean((0, 1)), img[10:22, -4:-1].mean((0, 1))
     assert (left[1] > left[0]) != (right[1] > right[0])          # one side is green-ish, the other red-ish
+    # the image is developed on the device (prt_render_image): same as dividing the RGBW film on the host
+    rp = scene.integrator().render_params(scene)
+    film, _ = scene.device().render_path(rp, seed=1, spp=8)
+    w = film[..., 3:4]
+    host = np.where(w > 0, film[..., :3] / np.maximum(w, 1e-30), 0.0)
+    assert np.allclose(img, host, rtol=2e-6, atol=1e-7)
 
 
 def test_heightfield_lbvh_against_oracle(orc):

@@ -236,6 +236,19 @@ def test_c_oracle_equals_python_transliteration(orc, name, order):
     assert np.allclose(buf_c, buf_p, rtol=1e-6, atol=1e-15)
 
 
+def test_pulse_shape_oracle_equals_the_prototype_echo_sum():
+    """oracle/pyref.pulse_shape (checker of the f4 kernel) against the literal per-echo sum of RayTracingV0.py:193-201."""
+    import pyref
+    fs, fc, sigma = 50e6, 3e6, 2e-7
+    echoes = [(10, 1.0), (200, -2.0), (399, 0.5)]
+    ch = np.zeros(400)
+    for i, a in echoes:
+        ch[i] = a
+    t = np.arange(400) / fs
+    lit = sum(a * np.sin(2 * np.pi * fc * (t - i / fs)) * np.exp(-((t - i / fs) ** 2) / sigma ** 2) for i, a in echoes)
+    assert np.abs(pyref.pulse_shape(ch, fs, fc, sigma) - lit).max() < 2e-7
+
+
 def test_pinned_pool_never_hands_out_a_live_buffer():
     """engine.Context.pinned_array: a result the caller still references (directly or through a derived view) is
     never reused (host logic; allocator faked, no GPU)."""
