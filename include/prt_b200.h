@@ -149,6 +149,18 @@ typedef struct {
     int32_t valid, prim, shape, recv, visible, reflect, k, survive;
     float   t, total_time, press, amp, atten, dir[3];
 } prt_seg_record;
+/* "next" row f2: the finite-difference loop of the driver (/root/reference/USMain.py:262-289: forward(rough),
+ * forward(rough + eps) = params['shape.bsdf.roughness'] = v; params.update(); simulate_acquisition_parallel).
+ * Traces n_values (<= PRT_MAX_VARIANTS) acquisitions that differ in ONE ultrasound_bsdf parameter
+ * (param_index 0 = impedance, 1 = roughness; CustomBSDF.py:12-18) of the materials in material_mask (bit = material
+ * id; the driver's key 'shape.bsdf.roughness' addresses every ultrasound_bsdf at once), with common random numbers
+ * (same seed, same per-path PCG32 streams), into channel_bufs [n_values][n_a][n_e][T].  The scene's stored
+ * parameter is not modified.  stats: nullable, [n_values]; kernel_ms / total_ms are those of the whole call. */
+#define PRT_MAX_VARIANTS 16
+int prt_acquire_variants(prt_scene *, const prt_acq_params *, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                         uint32_t sample_stride, uint64_t material_mask, int param_index, const double *values,
+                         uint32_t n_values, float *channel_bufs, float *tx_delays /*nullable*/,
+                         prt_acq_stats *stats /*nullable*/);
 int prt_acquire_trace(prt_scene *, const prt_acq_params *, uint64_t seed, uint32_t spp_total,
                       const uint64_t *path_idx, uint64_t n, prt_seg_record *rec);
 

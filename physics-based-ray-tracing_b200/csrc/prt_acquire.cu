@@ -33,6 +33,9 @@ struct AcqDev {
     uint32_t spp_total, s_offset, s_stride;
     uint64_t n_s, total;   // samples per (a,e) for this call, total paths of this call
     int a_first, a_count;  // angle range of this LAUNCH (prt_acquire pipelines one launch per angle with its D2H slice)
+    unsigned long long var_mask;   // prt_acquire_variants: materials (bit = id) whose parameter is overridden in this launch
+    int var_index;
+    float var_value;
     float *buf, *tx;
     unsigned long long *stats;  // {paths, segments, rays, deposits, misses}
 };
@@ -96,8 +99,13 @@ __device__ __forceinline__ bool segment(const AcqDev &P, const DPrim *prims, Pat
     const float3 md = -ps.d;
     const float3 wi = mk3(dot(md, h.fs), dot(md, h.ft), dot(md, h.ns));          // si.wi
     const DMaterial &mat = P.sc.mats[h.material];
+    float mZ = __ldg(&mat.p[0]), mA = __ldg(&mat.p[1]);                          // impedance, roughness (CB:12-18)
+    if ((P.var_mask >> (h.material & 63)) & 1ull) {                                             // finite-difference variant (USMain.py:264)
+        if (P.var_index == 0) mZ = P.var_value;
+        else mA = P.var_value;
+    }
     float3 dir; float pdf, a_resp; bool reflect;
-    ultra_bsdf_sample(wi, h.ng, h.ns, __ldg(&mat.p[0]), __ldg(&mat.p[1]), s1, s2, dir, pdf, a_resp, reflect);   // CI:175 / 338
+    ultra_bsdf_sample(wi, h.ng, h.ns, mZ, mA, s1, s2, dir, pdf, a_resp, reflect);   // CI:175 / 338
     const float cos_theta = dot(h.ns, md);                                       // CI:176 / 340
     ps.amp *= a_resp * cos_theta * fmaxf(pdf, 1e-6f);                            // CI:177 / 341
     // CI:124-133: alpha = |acos(dot)|; w_i = 1 (alpha <= alpha_m), linear ramp to 0 at alpha_c, else 0.  acos is
@@ -263,6 +271,9 @@ static int fill_params(prt_scene *s, const prt_acq_params *p, uint64_t seed, uin
     P.total = P.n_s * (uint64_t) p->n_angles * (uint64_t) p->n_elements;
     P.a_first = 0;
     P.a_count = p->n_angles;
+    P.var_mask = 0ull;
+    P.var_index = 0;
+    P.var_value = 0.0f;
     P.buf = nullptr;
     P.tx = nullptr;
     P.stats = nullptr;
@@ -398,6 +409,85 @@ int prt_acquire(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t s
         stats->_pad = 0;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    return PRT_OK;
+}
+
+// "next" row f2: the driver's finite-difference loop (USMain.py:262-289) runs f(rough) and
+// f(rough + eps) as two full acquisitions with a parameter patch in between.  Here all variants of ONE material
+// parameter are traced in one call: same seed and per-path PCG32 streams for every variant (common random numbers,
+// so the difference of two planes is not buried in Monte-Carlo noise), no parameter upload or BVH touch in between,
+// one zero-fill, one result transfer.  The override travels in the kernel parameter block.
+int prt_acquire_variants(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                         uint32_t sample_stride, uint64_t material_mask, int param_index, const double *values, uint32_t n_values,
+                         float *channel_bufs, float *tx_delays, prt_acq_stats *stats) {
+    PRT_REQUIRE(s && p && channel_bufs && values, "prt_acquire_variants: null argument");
+    PRT_REQUIRE(n_values >= 1 && n_values <= PRT_MAX_VARIANTS, "prt_acquire_variants: 1..PRT_MAX_VARIANTS values");
+    if (!s->committed) { set_error("prt_acquire_variants: scene not committed"); return PRT_ERR_STATE; }
+    PRT_REQUIRE(material_mask != 0 && (param_index == 0 || param_index == 1),
+                "prt_acquire_variants: empty material mask / parameter index out of range (0 = impedance, 1 = roughness)");
+    PRT_REQUIRE(s->mats.size() <= 64, "prt_acquire_variants: more than 64 materials");
+    for (size_t m = 0; m < 64; m++)
+        if ((material_mask >> m) & 1ull)
+            PRT_REQUIRE(m < s->mats.size() && s->mats[m].kind == PRT_MAT_ULTRA, "prt_acquire_variants: mask selects a material that is not an ultrasound_bsdf");
+    std::lock_guard<std::mutex> lk(s->ctx->mtx);
+    prt_context *c = s->ctx;
+    PRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    AcqDev P;
+    int rc = fill_params(s, p, seed, spp_total, sample_offset, sample_stride, P, st);
+    if (rc) return rc;
+    const size_t n_buf = (size_t) p->n_angles * p->n_elements * (size_t) p->time_samples;
+    const size_t n_tx = (size_t) p->n_angles * p->n_elements;
+    rc = ensure_scratch(c, n_buf * n_values, n_tx, (size_t) p->n_angles);
+    if (rc) return rc;
+    cudaEvent_t e0, e1, e2;
+    PRT_CUDA(cudaEventCreate(&e0)); PRT_CUDA(cudaEventCreate(&e1)); PRT_CUDA(cudaEventCreate(&e2));
+    PRT_CUDA(cudaEventRecord(e0, st));
+    PRT_CUDA(cudaMemsetAsync(c->acc_dev, 0, sizeof(float) * n_buf * n_values, st));
+    PRT_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(uint64_t) * 8 * PRT_MAX_VARIANTS, st));
+    unsigned launches = 0;
+    for (uint32_t v = 0; v < n_values; v++) {
+        AcqDev Q = P;
+        Q.buf = c->acc_dev + v * n_buf;
+        Q.tx = v == 0 ? c->aux_dev : nullptr;
+        Q.stats = reinterpret_cast<unsigned long long *>(c->stats_dev) + 8 * v;
+        Q.var_mask = material_mask;
+        Q.var_index = param_index;
+        Q.var_value = (float) values[v];
+        for (int a = 0; a < p->n_angles; a++) {       // one launch per steering angle, as in prt_acquire_dev
+            Q.a_first = a;
+            Q.a_count = 1;
+            rc = launch_acquire(c, Q, st);
+            if (rc) return rc;
+            launches++;
+        }
+    }
+    PRT_CUDA(cudaEventRecord(e1, st));
+    cudaPointerAttributes attr;
+    const bool pinned_dst = cudaPointerGetAttributes(&attr, channel_bufs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    float *pin = reinterpret_cast<float *>(c->pinned);
+    PRT_CUDA(cudaMemcpyAsync(pinned_dst ? channel_bufs : pin, c->acc_dev, sizeof(float) * n_buf * n_values, cudaMemcpyDeviceToHost, st));
+    PRT_CUDA(cudaMemcpyAsync(pin + n_buf * n_values, c->aux_dev, sizeof(float) * n_tx, cudaMemcpyDeviceToHost, st));
+    uint64_t hs[8 * PRT_MAX_VARIANTS];
+    PRT_CUDA(cudaMemcpyAsync(hs, c->stats_dev, sizeof hs, cudaMemcpyDeviceToHost, st));
+    PRT_CUDA(cudaEventRecord(e2, st));
+    PRT_CUDA(cudaStreamSynchronize(st));
+    if (!pinned_dst) memcpy(channel_bufs, pin, sizeof(float) * n_buf * n_values);
+    if (tx_delays) memcpy(tx_delays, pin + n_buf * n_values, sizeof(float) * n_tx);
+    if (stats) {
+        float k_ms = 0.0f, t_ms = 0.0f;
+        PRT_CUDA(cudaEventElapsedTime(&k_ms, e0, e1));
+        PRT_CUDA(cudaEventElapsedTime(&t_ms, e0, e2));
+        for (uint32_t v = 0; v < n_values; v++) {
+            const uint64_t *h = hs + 8 * v;
+            stats[v].paths = h[0]; stats[v].segments = h[1]; stats[v].rays = h[2]; stats[v].deposits = h[3]; stats[v].misses = h[4];
+            stats[v].kernel_ms = k_ms; stats[v].total_ms = t_ms;     // of the whole call
+            stats[v].launches = launches;
+            stats[v]._pad = 0;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return PRT_OK;
 }
 

@@ -12,7 +12,7 @@
 #include "prt_device.cuh"
 
 #ifndef PRT_MEGA_BVH8
-#define PRT_MEGA_BVH8 1
+#define PRT_MEGA_BVH8 0
 #endif
 
 namespace prt {

@@ -138,7 +138,7 @@ int prt_create(int device, prt_context **out) {
     PRT_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     PRT_CUDA(cudaEventCreateWithFlags(&c->slice_done[0], cudaEventDisableTiming));
     PRT_CUDA(cudaEventCreateWithFlags(&c->slice_done[1], cudaEventDisableTiming));
-    PRT_CUDA(cudaMalloc(&c->stats_dev, sizeof(uint64_t) * 8));
+    PRT_CUDA(cudaMalloc(&c->stats_dev, sizeof(uint64_t) * 8 * PRT_MAX_VARIANTS));
     *out = c;
     return PRT_OK;
 }

@@ -52,7 +52,18 @@ static constexpr int WF_SHADE_THREADS = 256;
 #ifndef WF_TRACE_MINB
 #define WF_TRACE_MINB 8                   // min resident CTAs per SM the trace kernels are compiled for
 #endif
+#ifndef WF_QCHUNK
+#define WF_QCHUNK 32                      // shading-queue entries a trace warp reserves per atomic (0: one atomic per retire event)
+#endif
+#ifndef WF_PREFETCH
+#define WF_PREFETCH 0                     // bit 0: ray records of a reserved chunk -> L2; bit 1: next node -> L1; bit 2: triangles -> L1
+#endif
+static_assert(WF_QCHUNK == 0 || WF_QCHUNK >= 32, "a retire event appends up to 32 entries: one fresh chunk must hold them");
+static constexpr uint32_t WF_HOLE = 0xffffffffu;   // unused tail of a warp's reserved queue chunk
 enum { C_EXT = 0, C_MAT = 1, C_SH = 4, C_HEAD_EXT = 8, C_HEAD_SH = 12 };
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ray record, 4 x float4, written by the producer at the ray's queue position:
 //   r0 = origin xyz, bits(path slot)          r1 = direction xyz, tmax
@@ -174,6 +185,12 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
     __shared__ DPrim sprims[MAX_SMEM_PRIMS];
     __shared__ int s_owner[WF_TRACE_THREADS], s_win[WF_TRACE_THREADS];
     __shared__ unsigned s_tmin[WF_TRACE_THREADS];
+#if WF_QCHUNK
+    // warp-private cursors into the shading queues: a warp reserves WF_QCHUNK entries per atomic and fills them over
+    // several retire events, so retiring a ray does not wait for a round trip to the L2 atomic unit
+    __shared__ int s_qcur[WF_TRACE_THREADS / 32][2 * WF_QUEUES];
+    if (!ANY && (threadIdx.x & 31) < 2 * WF_QUEUES) s_qcur[threadIdx.x >> 5][threadIdx.x & 31] = 0;
+#endif
     const DScene &sc = P.sc;
     const DPrim *prims = sprims;
     if (sc.n_prims > MAX_SMEM_PRIMS) prims = sc.prims;
@@ -227,11 +244,35 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                     B.ST[8 * (size_t) slot + 6] = make_float4(t, b1, b2, __int_as_float(id));
                     if (id >= 0) n_valid++;
                 }
+#if WF_QCHUNK
+                int *qc = s_qcur[threadIdx.x >> 5];
+#pragma unroll
+                for (int k = 0; k < WF_QUEUES; k++) {
+                    const unsigned m = __ballot_sync(FULL, qi == k);
+                    if (!m) continue;
+                    const int cnt = __popc(m), rank = __popc(m & lanemask_lt());
+                    int next = qc[2 * k], end = qc[2 * k + 1];
+                    const int room = end - next;
+                    int fresh = 0;
+                    if (cnt > room) {      // WF_QCHUNK >= 32 >= cnt: one new chunk always suffices
+                        if (lane == 0) fresh = atomicAdd(C + C_MAT + k, WF_QCHUNK);
+                        fresh = __shfl_sync(FULL, fresh, 0);
+                    }
+                    if (qi == k) B.q_mat[k][rank < room ? next + rank : fresh + (rank - room)] = slot;
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (cnt > room) { qc[2 * k] = fresh + (cnt - room); qc[2 * k + 1] = fresh + WF_QCHUNK; }
+                        else qc[2 * k] = next + cnt;
+                    }
+                    __syncwarp();
+                }
+#else
 #pragma unroll
                 for (int k = 0; k < WF_QUEUES; k++) {
                     const int q = wf_reserve(C + C_MAT + k, qi == k);
                     if (qi == k) B.q_mat[k][q] = slot;
                 }
+#endif
             } else if (fin && best < 0 && best_prim < 0) {
                 const float4 c = B.SHC[qpos];
                 const float w = R.r2[qpos].w;
@@ -260,6 +301,15 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                         dry = true;
                         break;
                     }
+#if WF_PREFETCH & 1
+                    // the warp consumes this chunk a few rays per iteration: pull its records towards L2 now
+                    for (int i = pool_next + lane; i < pool_end; i += 32) {
+                        prefetch_l2(R.r0 + i);
+                        prefetch_l2(R.r2 + i);
+                        prefetch_l2(R.r3 + i);
+                        if (sc.n_prims > 0 || ANY) prefetch_l2(R.r1 + i);
+                    }
+#endif
                 }
                 const int avail = pool_end - pool_next;
                 const int rank = __popc(need & lanemask_lt());
@@ -319,6 +369,22 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
             const uint32_t hm = bvh8_node(sc.nodes8, ng.x + rel, r8, tbest, child_base, tri_base, imask);
             ng = make_uint2(child_base, (hm & 0xff000000u) | imask);
             tg = make_uint2(tri_base, hm & 0x00ffffffu);
+#if WF_PREFETCH & 4
+            if (tg.y) {     // the triangle tests below may be dealt to other lanes: start the fetch from the owner now
+                const float4 *tv = sc.tri_v8 + 3 * (size_t) (tg.x + (uint32_t) (31 - __clz(tg.y)));
+                prefetch_l1(tv);
+                prefetch_l1(tv + 2);
+            }
+#endif
+#if WF_PREFETCH & 2
+            if (ng.y > 0x00ffffffu) {   // the node this lane visits next: its fetch overlaps the triangle phase
+                const int nb = 31 - __clz(ng.y);
+                const uint32_t si = (uint32_t) (nb - 24) ^ (r8.octinv4 & 0xffu);
+                const float4 *nn = sc.nodes8 + 5 * (size_t) (ng.x + __popc(ng.y & 0xffu & ~(0xffffffffu << si)));
+                prefetch_l1(nn);
+                prefetch_l1(nn + 4);
+            }
+#endif
         }
         // ---- the triangles those nodes yielded ----
         const unsigned mT = __ballot_sync(FULL, tg.y != 0u);
@@ -402,6 +468,14 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
             else busy = false;
         }
     }
+#if WF_QCHUNK
+    if (!ANY) {     // unused tail of the last reserved chunk of every queue: mark as holes for the shading kernels
+        const int *qc = s_qcur[threadIdx.x >> 5];
+#pragma unroll
+        for (int k = 0; k < WF_QUEUES; k++)
+            for (int i = qc[2 * k] + lane; i < qc[2 * k + 1]; i += 32) B.q_mat[k][i] = WF_HOLE;
+    }
+#endif
     wf_add_stat(P, 2, n_rays);
     if (ANY) wf_add_stat(P, 3, n_rays);
     else wf_add_stat(P, 1, n_valid);
@@ -424,8 +498,8 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(co
         ShadowReq sr;
         sr.want = false;
         PtState st;
-        if (i < n) {
-            slot = q[i];
+        if (i < n) slot = q[i];
+        if (i < n && slot != WF_HOLE) {
             wf_load_state(B, slot, st);
             const float4 hv = B.ST[8 * (size_t) slot + 6];
             const int id = __float_as_int(hv.w);
@@ -494,7 +568,9 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
     const int bounces = P.max_depth > 1 ? P.max_depth : 1;
     const size_t cnt_bytes = (sizeof(int) * WF_CSTRIDE * (size_t) (bounces + 1) + 255) & ~(size_t) 255;
     const size_t per_slot = 16 * (8 + 8 + 4 + 1) + 4 * WF_QUEUES;
-    const size_t need = (size_t) cap * per_slot + cnt_bytes;
+    // every trace warp may leave one partly used chunk per queue behind (holes): room for them on top of `cap` entries
+    const size_t q_slack = (size_t) c->sm_count * 64 * (WF_QCHUNK ? WF_QCHUNK : 1);
+    const size_t need = (size_t) cap * per_slot + 4 * WF_QUEUES * q_slack + cnt_bytes;
     if (need > c->wf_cap) {
         if (c->wf_dev) cudaFree(c->wf_dev);
         c->wf_dev = nullptr;
@@ -512,7 +588,7 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
         for (int k = 0; k < 2; k++) { B.ext[k].r0 = take4(); B.ext[k].r1 = take4(); B.ext[k].r2 = take4(); B.ext[k].r3 = take4(); }
         B.sh.r0 = take4(); B.sh.r1 = take4(); B.sh.r2 = take4(); B.sh.r3 = take4();
         B.SHC = take4();
-        for (int k = 0; k < WF_QUEUES; k++) B.q_mat[k] = reinterpret_cast<uint32_t *>(take(4 * cap));
+        for (int k = 0; k < WF_QUEUES; k++) B.q_mat[k] = reinterpret_cast<uint32_t *>(take(4 * (cap + q_slack)));
     }
     B.cap = (uint32_t) cap;
     B.L = (uint32_t) L;

@@ -166,6 +166,25 @@ class DeviceScene:
                                  C.byref(st)), "prt_acquire")
         return buf, tx, st.as_dict()
 
+    def acquire_variants(self, params: AcqParams, materials, index: int, values, seed: int = 0, spp: int = 1,
+                         sample_offset: int = 0, sample_stride: int = 1):
+        """The finite-difference loop of USMain.py:262-289 in one call: one acquisition per value of ONE ultrasound_bsdf
+        parameter (index 0 impedance, 1 roughness) of ``materials`` (an id or several), common random numbers.
+        Returns (bufs [V,n_a,n_e,T], tx, [stats])."""
+        mask = 0
+        for m in np.atleast_1d(materials):
+            mask |= 1 << int(m)
+        vals = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
+        if not 1 <= vals.size <= capi.MAX_VARIANTS:
+            raise ValueError(f"acquire_variants: 1..{capi.MAX_VARIANTS} values")
+        ps = capi.make_acq_params(params)
+        bufs = self.ctx.pinned_array((vals.size, params.n_angles, params.n_elements, params.time_samples), np.float32)
+        tx = np.empty((params.n_angles, params.n_elements), dtype=np.float32)
+        st = (capi.AcqStatsC * vals.size)()
+        check(self.L.prt_acquire_variants(self.h, C.byref(ps), seed, spp, sample_offset, sample_stride, mask, int(index),
+                                          dptr(vals), vals.size, fptr(bufs), fptr(tx), st), "prt_acquire_variants")
+        return bufs, tx, [x.as_dict() for x in st]
+
     def acquire_dev(self, params: AcqParams, buf_ptr: int, tx_ptr: int = 0, stats_ptr: int = 0, stream: int = 0,
                     seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1):
         """Device-buffer entry point (accumulates into ``buf_ptr`` on ``stream``, asynchronous)."""

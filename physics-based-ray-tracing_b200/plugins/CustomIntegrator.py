@@ -123,6 +123,29 @@ class UltraIntegrator(mi.SamplingIntegrator):
         print("Channel buffer shape:", self.channel_buf.shape)
         return True
 
+    def simulate_acquisition_variants(self, scene, key, values):
+        """Extension for the driver's finite-difference loop (USMain.py:262-289): what
+        ``params[key] = v; params.update(); simulate_acquisition_parallel(scene)`` yields for every v in ``values``,
+        traced in ONE library call with common random numbers (prt_acquire_variants).  ``key`` is a mi.traverse key
+        such as 'shape.bsdf.roughness'.  Returns ``[len(values), n_angles, n_elements, time_samples]`` float32; the
+        scene's own parameter is left untouched."""
+        targets = mi.traverse(scene)._targets.get(key)
+        if not targets:
+            raise KeyError(key)
+        index = targets[0][1]
+        if any(i != index for _, i in targets):
+            raise ValueError(f"{key}: mixed parameters")
+        p = self.acq_params(scene)
+        p.quirk_flags = self.quirk_flags
+        bufs, tx, st = scene.device().acquire_variants(p, [m for m, _ in targets], index, values, seed=self.seed,
+                                                       spp=max(int(self.samples_per_element), 1))
+        self.last_stats = st
+        self.transmission_delays_buf = tx.reshape(-1)
+        if self.shape_pulse:
+            from prt_b200.engine import pulse_shape
+            bufs = pulse_shape(bufs, self.fs, self.frequency, wave_cycles=self.wave_cycles, context=scene.device().ctx)
+        return bufs
+
     def traverse(self, callback):
         callback.put_parameter('pitch', self.pitch, mi.ParamFlags.Differentiable)
 

