@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128) k_bvh8_level(int begin, int end, int *__r
             const int cnt = sub_count(ranges, c[k].ref);
             const int first = c[k].ref < 0 ? ~c[k].ref : ranges[c[k].ref].x;
             meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t) off;
-            for (int j = 0; j < cnt; j++) {
+            for (int j = 0; nodes8 && j < cnt; j++) {
                 const size_t dst = (size_t) tri_base + off + j, sidx = (size_t) first + j;
                 tri_v8[3 * dst] = tri_v_sorted[3 * sidx];
                 tri_v8[3 * dst + 1] = tri_v_sorted[3 * sidx + 1];
@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(128) k_bvh8_level(int begin, int end, int *__r
             off += cnt;
         }
     }
+    if (!nodes8) return;     // counting pass: only the task list and the two counters are produced
     auto pack4 = [](const uint32_t *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
     float4 *out = nodes8 + 5 * (size_t) idx;
     out[0] = make_float4(plo[0], plo[1], plo[2], __uint_as_float(eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24)));
@@ -237,37 +238,42 @@ int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, cons
         *out_levels = 1;
         return PRT_OK;
     }
-    const size_t cap = (size_t) n;                 // every wide node opens a distinct binary node with > 3 triangles
-    float4 *tmp_nodes = nullptr, *tri_v8 = nullptr;
+    // Two passes over the same level-by-level loop: the first only counts (the wide tree has ~n/7 nodes, but the safe
+    // a-priori bound is n: an 800 MB scratch array at 10 M triangles whose cudaFree alone cost 0.7 s), the second writes
+    // into exactly sized arrays (the node count does not depend on the order in which the atomics hand out storage).
+    const size_t cap = (size_t) n;                 // tasks: every wide node opens a distinct binary node with > 3 triangles
+    float4 *nodes8 = nullptr, *tri_v8 = nullptr;
     uint32_t *tri8_sorted = nullptr;
     int *src = nullptr, *counters = nullptr;
-    PRT_CUDA(cudaMalloc(&tmp_nodes, sizeof(float4) * 5 * cap));
-    PRT_CUDA(cudaMalloc(&tri_v8, sizeof(float4) * 3 * (size_t) n));
-    PRT_CUDA(cudaMalloc(&tri8_sorted, sizeof(uint32_t) * (size_t) n));
     PRT_CUDA(cudaMalloc(&src, sizeof(int) * cap));
     PRT_CUDA(cudaMalloc(&counters, sizeof(int) * 2));
-    const int init[2] = { 1, 0 };
-    PRT_CUDA(cudaMemcpyAsync(counters, init, sizeof init, cudaMemcpyHostToDevice, st));
-    PRT_CUDA(cudaMemsetAsync(src, 0, sizeof(int), st));   // task 0 = binary root (node 0)
-    int begin = 0, end = 1, levels = 0;
-    while (begin < end) {
-        const int cnt = end - begin;
-        k_bvh8_level<<<(cnt + 127) / 128, 128, 0, st>>>(begin, end, src, nodes2, children, ranges, tri_v_sorted, tmp_nodes, tri_v8,
-                                                        tri8_sorted, counters);
-        int h[2];
-        PRT_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, st));
-        PRT_CUDA(cudaStreamSynchronize(st));
-        begin = end;
-        end = h[0];
-        levels++;
-        if (levels > 256) { set_error("build_bvh8: runaway depth"); return PRT_ERR_STATE; }
+    int end = 1, levels = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            PRT_CUDA(cudaMalloc(&nodes8, sizeof(float4) * 5 * (size_t) end));
+            PRT_CUDA(cudaMalloc(&tri_v8, sizeof(float4) * 3 * (size_t) n));
+            PRT_CUDA(cudaMalloc(&tri8_sorted, sizeof(uint32_t) * (size_t) n));
+        }
+        const int init[2] = { 1, 0 };
+        PRT_CUDA(cudaMemcpyAsync(counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+        PRT_CUDA(cudaMemsetAsync(src, 0, sizeof(int), st));   // task 0 = binary root (node 0)
+        int begin = 0;
+        end = 1;
+        levels = 0;
+        while (begin < end) {
+            const int cnt = end - begin;
+            k_bvh8_level<<<(cnt + 127) / 128, 128, 0, st>>>(begin, end, src, nodes2, children, ranges, tri_v_sorted, nodes8, tri_v8,
+                                                            tri8_sorted, counters);
+            int h[2];
+            PRT_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, st));
+            PRT_CUDA(cudaStreamSynchronize(st));
+            begin = end;
+            end = h[0];
+            levels++;
+            if (levels > 256) { set_error("build_bvh8: runaway depth"); return PRT_ERR_STATE; }
+        }
+        PRT_CUDA(cudaGetLastError());
     }
-    PRT_CUDA(cudaGetLastError());
-    float4 *nodes8 = nullptr;
-    PRT_CUDA(cudaMalloc(&nodes8, sizeof(float4) * 5 * (size_t) end));
-    PRT_CUDA(cudaMemcpyAsync(nodes8, tmp_nodes, sizeof(float4) * 5 * (size_t) end, cudaMemcpyDeviceToDevice, st));
-    PRT_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp_nodes);
     cudaFree(src);
     cudaFree(counters);
     *out_nodes8 = nodes8;

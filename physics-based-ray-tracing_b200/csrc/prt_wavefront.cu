@@ -55,6 +55,9 @@ static constexpr int WF_SHADE_THREADS = 256;
 #ifndef WF_QCHUNK
 #define WF_QCHUNK 32                      // shading-queue entries a trace warp reserves per atomic (0: one atomic per retire event)
 #endif
+#ifndef WF_SLOT_SHADE
+#define WF_SLOT_SHADE 70                  // a shading kernel walks the path SLOTS in order (picking its material by the per-slot tag)
+#endif                                    // when its queue holds more than this percentage of the batch's slots, else the compacted queue; 0: never
 #ifndef WF_PREFETCH
 #define WF_PREFETCH 0                     // bit 0: ray records of a reserved chunk -> L2; bit 1: next node -> L1; bit 2: triangles -> L1
 #endif
@@ -84,6 +87,7 @@ struct WfBuf {
     WfRays sh;       // shadow rays of the current bounce
     float4 *SHC;     // shadow rays: NEE contribution rgb
     uint32_t *q_mat[WF_QUEUES];
+    uint8_t *tag;    // [cap] per slot: 1 + shading queue of the hit waiting to be shaded, 0 = nothing to shade
     int *cnt;        // [bounces + 1][WF_CSTRIDE]
     uint32_t cap, L, n_layers, j0;
 };
@@ -244,6 +248,9 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                     B.ST[8 * (size_t) slot + 6] = make_float4(t, b1, b2, __int_as_float(id));
                     if (id >= 0) n_valid++;
                 }
+#if WF_SLOT_SHADE
+                if (fin) B.tag[slot] = (uint8_t) (qi + 1);
+#endif
 #if WF_QCHUNK
                 int *qc = s_qcur[threadIdx.x >> 5];
 #pragma unroll
@@ -488,8 +495,22 @@ template <int QI>
 __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(const PtDev P, const WfBuf B, const int bounce) {
     int *C = B.cnt + bounce * WF_CSTRIDE;
     int *Cn = C + WF_CSTRIDE;
-    const int n = C[C_MAT + QI];
+    // Two ways to find this kernel's paths.  The compacted queue (slot ids appended by the trace kernel, ballot +
+    // prefix popcount per retire event) costs nothing for sparse materials, but it is filled in RETIRE order, which
+    // drifts towards a random permutation of the slots within ~5 bounces: path state is then gathered from scattered
+    // DRAM pages and the same kernel runs 2x slower (profiles/r01_summary.md).  When most of the batch is in this
+    // queue anyway, walk the SLOTS in order instead and pick this material by its tag: state becomes a sequential
+    // stream of 128-byte records and the next bounce's ray queue comes out slot-coherent at warp granularity.
+    const int nq = C[C_MAT + QI];
     const uint32_t *q = B.q_mat[QI];
+#if WF_SLOT_SHADE
+    const int ns = (int) (B.n_layers * B.L);
+    const bool by_slot = (long long) nq * 100 > (long long) ns * WF_SLOT_SHADE;
+    const int n = by_slot ? ns : nq;
+#else
+    const bool by_slot = false;
+    const int n = nq;
+#endif
     const WfRays Rn = B.ext[(bounce + 1) & 1];
     for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
         const int i = i0 + threadIdx.x;
@@ -498,8 +519,17 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(co
         ShadowReq sr;
         sr.want = false;
         PtState st;
-        if (i < n) slot = q[i];
-        if (i < n && slot != WF_HOLE) {
+        bool mine = false;
+        if (i < n) {
+            if (by_slot) {
+                slot = (uint32_t) i;
+                mine = B.tag[i] == (uint8_t) (QI + 1);
+            } else {
+                slot = q[i];
+                mine = slot != WF_HOLE;
+            }
+        }
+        if (mine) {
             wf_load_state(B, slot, st);
             const float4 hv = B.ST[8 * (size_t) slot + 6];
             const int id = __float_as_int(hv.w);
@@ -508,6 +538,9 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(co
             else fill_prim_hit(P.sc.prims[id], id, st.o, st.d, hv.x, h);
             live = pt_shade(P, st, h, true, sr);
             wf_store_state(B, slot, st);
+#if WF_SLOT_SHADE
+            if (!live) B.tag[slot] = 0;      // a live path's tag is rewritten when its next ray retires
+#endif
         }
         const int j = wf_reserve(C + C_SH, sr.want);
         if (sr.want) {
@@ -570,7 +603,7 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
     const size_t per_slot = 16 * (8 + 8 + 4 + 1) + 4 * WF_QUEUES;
     // every trace warp may leave one partly used chunk per queue behind (holes): room for them on top of `cap` entries
     const size_t q_slack = (size_t) c->sm_count * 64 * (WF_QCHUNK ? WF_QCHUNK : 1);
-    const size_t need = (size_t) cap * per_slot + 4 * WF_QUEUES * q_slack + cnt_bytes;
+    const size_t need = (size_t) cap * (per_slot + 1) + 4 * WF_QUEUES * q_slack + cnt_bytes;
     if (need > c->wf_cap) {
         if (c->wf_dev) cudaFree(c->wf_dev);
         c->wf_dev = nullptr;
@@ -589,6 +622,7 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
         B.sh.r0 = take4(); B.sh.r1 = take4(); B.sh.r2 = take4(); B.sh.r3 = take4();
         B.SHC = take4();
         for (int k = 0; k < WF_QUEUES; k++) B.q_mat[k] = reinterpret_cast<uint32_t *>(take(4 * (cap + q_slack)));
+        B.tag = reinterpret_cast<uint8_t *>(take(cap));
     }
     B.cap = (uint32_t) cap;
     B.L = (uint32_t) L;
@@ -605,6 +639,9 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
         B.j0 = (uint32_t) j0;
         B.n_layers = (uint32_t) (P.n_s - j0 < layers ? P.n_s - j0 : layers);
         PRT_CUDA(cudaMemsetAsync(B.cnt, 0, cnt_bytes, st));
+#if WF_SLOT_SHADE
+        PRT_CUDA(cudaMemsetAsync(B.tag, 0, (size_t) B.n_layers * L, st));
+#endif
         {
             ProfScope ps(c, PRT_KC_GENERATE, st);
             k_wf_generate<<<g_gen, WF_SHADE_THREADS, 0, st>>>(P, B);
