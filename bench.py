@@ -120,16 +120,19 @@ def cpu_oracle_rate(desc, params, spp: int, seed: int, threads: int):
     return st, dt
 
 
-def ncu_traffic(key: str):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json,
-    written by hand from profiles/*.txt); None when this workload has not been captured."""
+def ncu_entry(key: str) -> dict:
+    """What the committed `ncu --set full` capture of this workload's dominant kernel says (profiles/traffic.json,
+    transcribed from profiles/*_ncu_*.txt): DRAM bytes per launch, warp instructions per ray.  {} if not captured."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
-        return None, None
+        return {}
     with open(path) as fh:
-        d = json.load(fh)
-    e = d.get(key)
-    return (e["dram_bytes_per_launch"], e["source"]) if e else (None, None)
+        return json.load(fh).get(key.partition(":")[0] if key.startswith("heightfield") else key, {})
+
+
+def ncu_traffic(key: str):
+    e = ncu_entry(key)
+    return (e.get("dram_bytes_per_launch"), e.get("source")) if e else (None, None)
 
 
 WF_RAY_RECORD_BYTES = 64 + 16      # ray record read (4 x float4) + hit record written, per closest-hit query
@@ -250,7 +253,7 @@ def pt_measure(args, workload, steps, warmup, rank, world, device, e2e_steps, cp
         dom, dom_ms = "prt::k_render_path", mk["ms"] / max(mk["launches"], 1)
         alg_bytes = int(st_local[2]) * bvh_min_bytes(n_tris) / max(mk["launches"], 1) + film.numel() * 4
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    traffic, traffic_src = ncu_traffic(workload.partition(":")[0])
+    traffic, traffic_src = ncu_traffic(workload)
     n_launch = sum(c["launches"] for c in classes.values())
     line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -277,6 +280,12 @@ def pt_measure(args, workload, steps, warmup, rank, world, device, e2e_steps, cp
                                  f"fetches, SURVEY 8(d), + {WF_RAY_RECORD_BYTES} B ray/hit records) / its CUDA-event time; "
                                  + ("scene lives on chip" if n_tris < 100000 else "scene >> L2: fetches go to HBM")},
             "clocks": clk}
+    wipr = ncu_entry(workload).get("warp_inst_per_ray")
+    if wipr and clk.get("sm_mhz") and tc["launches"]:
+        ray_rate = closest_local / (tc["ms"] * 1e-3)          # closest-hit rays per second inside k_wf_trace<false>
+        peak_issue = 148 * 4 * clk["sm_mhz"] * 1e6
+        line["issue"] = {"warp_inst_per_ray": wipr, "achieved_ginst_s": ray_rate * wipr / 1e9, "peak_ginst_s": peak_issue / 1e9,
+                         "frac": ray_rate * wipr / peak_issue, "source": ncu_entry(workload).get("source")}
     if cpu_baseline:
         import orc_py
         threads = os.cpu_count() or 1
@@ -514,14 +523,22 @@ def main():
                                   "stays in L2: this configuration is instruction-issue bound, not HBM bound (see `issue`)")},
             "clocks": clk,
         }
-        # instruction-issue view (the binding limit for analytic scenes): ncu-measured warp instructions per
-        # segment (profiles/) x segments/s against 4 schedulers x 148 SMs x clock under load
-        inst_per_seg = float(os.environ.get("PRT_WARP_INST_PER_SEGMENT", "0") or 0)
-        if inst_per_seg > 0 and clk.get("sm_mhz"):
-            seg_rate = (segments / world / args.steps) / (k_ms * 1e-3)
+        # instruction-issue view (the binding limit when the scene lives on chip): warp instructions per ray from the
+        # committed ncu capture (profiles/traffic.json) x this run's rays/s, against 4 schedulers x 148 SMs x the SM
+        # clock sampled during the timed region
+        wipr = ncu_entry(args.workload).get("warp_inst_per_ray")
+        if wipr and clk.get("sm_mhz"):
+            ray_rate = rays_per_launch / (launch_ms * 1e-3)
             peak_issue = 148 * 4 * clk["sm_mhz"] * 1e6
-            line["issue"] = {"warp_inst_per_segment": inst_per_seg, "achieved_ginst_s": seg_rate / 32 * inst_per_seg / 1e9,
-                             "peak_ginst_s": peak_issue / 1e9, "frac": seg_rate / 32 * inst_per_seg / peak_issue}
+            line["issue"] = {"warp_inst_per_ray": wipr, "achieved_ginst_s": ray_rate * wipr / 1e9,
+                             "peak_ginst_s": peak_issue / 1e9, "frac": ray_rate * wipr / peak_issue,
+                             "source": ncu_entry(args.workload).get("source")}
+        if n_tris == 0 and clk.get("sm_mhz"):
+            # fp32 view of SURVEY 8(d): ~740 flop per segment (2 queries x 255 + UltraBSDF 150 + glue 80) on analytic scenes
+            seg_rate = (segments / world / max(acq["launches"], 1)) / (launch_ms * 1e-3)
+            peak_tf = 148 * 128 * 2 * clk["sm_mhz"] * 1e6 / 1e12
+            line["fp32"] = {"flop_per_segment": 740, "achieved_tflops": seg_rate * 740 / 1e12, "peak_tflops": peak_tf,
+                            "frac": seg_rate * 740 / 1e12 / peak_tf, "note": "SURVEY 8(d) estimate; sqrt/exp/sin/acos counted as 1"}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             st, dt = cpu_oracle_rate(desc, p, C1_SPP, 0, threads)
@@ -543,7 +560,8 @@ def main():
         cb = pt_measure(args, "cbox", 3, 3, rank, world, device, 2, False)
         if rank == 0:
             line["also"] = {"cbox": {k: cb[k] for k in ("value", "unit", "ms_per_step", "msamples_per_s", "e2e", "gpu_launches",
-                                                         "kernel", "kernel_ms", "kernel_classes", "roofline", "config")}}
+                                                         "kernel", "kernel_ms", "kernel_classes", "roofline", "issue", "config")
+                                     if k in cb}}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

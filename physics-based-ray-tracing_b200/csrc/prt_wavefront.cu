@@ -26,7 +26,9 @@
 //
 // All launches of a batch are enqueued back to back: queue lengths live in device memory (one counter block per
 // bounce, zeroed once), so the host never synchronises inside a batch.
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "prt_bvh8.cuh"
 #include "prt_internal.h"
@@ -699,6 +701,15 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
             launches++;
         }
         PRT_CUDA(cudaGetLastError());
+        if (getenv("PRT_WF_DEBUG")) {     // per-bounce queue lengths of this batch (profiling aid; synchronises)
+            std::vector<int> h(WF_CSTRIDE * (size_t) (bounces + 1));
+            PRT_CUDA(cudaMemcpyAsync(h.data(), B.cnt, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, st));
+            PRT_CUDA(cudaStreamSynchronize(st));
+            for (int b = 0; b < bounces; b++)
+                fprintf(stderr, "[prt wf] batch %u bounce %d: extend rays %d, shadow rays %d, shading queues %d / %d / %d\n", B.j0, b,
+                        h[b * WF_CSTRIDE + C_EXT], h[b * WF_CSTRIDE + C_SH], h[b * WF_CSTRIDE + C_MAT], h[b * WF_CSTRIDE + C_MAT + 1],
+                        h[b * WF_CSTRIDE + C_MAT + 2]);
+        }
     }
     c->last_launches = launches;
     return PRT_OK;

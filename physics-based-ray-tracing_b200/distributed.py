@@ -37,9 +37,27 @@ def allreduce_sum_(tensor):
     return tensor
 
 
+def _cached(dev_scene, key, make):
+    """Per-scene cache of device tensors reused across calls (no allocator traffic in the steady state)."""
+    cache = dev_scene.__dict__.setdefault("_shard_cache", {})
+    t = cache.get(key)
+    if t is None:
+        t = cache[key] = make()
+    return t
+
+
+def _to_pinned(dev_scene, tensor):
+    """Device tensor -> pooled page-locked numpy array (prt_host_alloc): one DMA, no pageable staging."""
+    import torch
+    host = dev_scene.ctx.pinned_array(tuple(tensor.shape), np.float32)
+    torch.from_numpy(host).copy_(tensor)
+    return host
+
+
 def acquire_sharded(dev_scene, params, seed: int, spp_total: int, to_host: bool = True, buf=None, stats=None):
     """Rank-local shard of an acquisition + all-reduce.  Returns (channel_buf, tx_delays, stats) with the
-    buffers on the host (numpy) if ``to_host`` else as torch CUDA tensors."""
+    buffers on the host (numpy, page-locked) if ``to_host`` else as torch CUDA tensors (owned by the scene's cache
+    unless passed in: the next call overwrites them)."""
     import torch
     dist, rank, world = _dist()
     device = torch.device("cuda", dev_scene.ctx.device)
@@ -47,14 +65,12 @@ def acquire_sharded(dev_scene, params, seed: int, spp_total: int, to_host: bool 
     shape = (params.n_angles, params.n_elements, params.time_samples)
     with torch.cuda.device(device):
         if buf is None:
-            buf = torch.zeros(shape, dtype=torch.float32, device=device)
-        else:
-            buf.zero_()
-        tx = torch.empty((params.n_angles, params.n_elements), dtype=torch.float32, device=device)
+            buf = _cached(dev_scene, ("acq", shape), lambda: torch.empty(shape, dtype=torch.float32, device=device))
+        buf.zero_()
+        tx = _cached(dev_scene, ("tx", shape[:2]), lambda: torch.empty(shape[:2], dtype=torch.float32, device=device))
         if stats is None:
-            stats = torch.zeros(8, dtype=torch.int64, device=device)
-        else:
-            stats.zero_()
+            stats = _cached(dev_scene, "stats", lambda: torch.empty(8, dtype=torch.int64, device=device))
+        stats.zero_()
         stream = torch.cuda.current_stream(device)
         dev_scene.acquire_dev(params, buf.data_ptr(), tx.data_ptr(), stats.data_ptr(), stream.cuda_stream, seed=seed,
                               spp=spp_total, sample_offset=off, sample_stride=stride)
@@ -63,7 +79,8 @@ def acquire_sharded(dev_scene, params, seed: int, spp_total: int, to_host: bool 
             dist.all_reduce(stats, op=dist.ReduceOp.SUM)
         if not to_host:
             return buf, tx, stats
-        hb, htx, hs = buf.cpu().numpy(), tx.cpu().numpy(), stats.cpu().numpy()
+        hb = _to_pinned(dev_scene, buf)
+        htx, hs = tx.cpu().numpy(), stats.cpu().numpy()
     st = dict(paths=int(hs[0]), segments=int(hs[1]), rays=int(hs[2]), deposits=int(hs[3]), misses=int(hs[4]))
     return hb, htx, st
 
@@ -77,13 +94,12 @@ def render_sharded(dev_scene, rp, seed: int, spp_total: int, to_host: bool = Tru
     off, stride, _ = shard_samples(spp_total, rank, world)
     with torch.cuda.device(device):
         if film is None:
-            film = torch.zeros((rp.height, rp.width, 4), dtype=torch.float32, device=device)
-        else:
-            film.zero_()
+            film = _cached(dev_scene, ("film", rp.height, rp.width),
+                           lambda: torch.empty((rp.height, rp.width, 4), dtype=torch.float32, device=device))
+        film.zero_()
         if stats is None:
-            stats = torch.zeros(8, dtype=torch.int64, device=device)
-        else:
-            stats.zero_()
+            stats = _cached(dev_scene, "stats", lambda: torch.empty(8, dtype=torch.int64, device=device))
+        stats.zero_()
         stream = torch.cuda.current_stream(device)
         dev_scene.render_path_dev(rp, film.data_ptr(), stats.data_ptr(), stream.cuda_stream, seed=seed, spp=spp_total,
                                   sample_offset=off, sample_stride=stride)
@@ -91,10 +107,11 @@ def render_sharded(dev_scene, rp, seed: int, spp_total: int, to_host: bool = Tru
             dist.all_reduce(film, op=dist.ReduceOp.SUM)
             dist.all_reduce(stats, op=dist.ReduceOp.SUM)
         if develop:
-            rgb = torch.empty((rp.height, rp.width, 3), dtype=torch.float32, device=device)
+            rgb = _cached(dev_scene, ("rgb", rp.height, rp.width),
+                          lambda: torch.empty((rp.height, rp.width, 3), dtype=torch.float32, device=device))
             dev_scene.develop_dev(film.data_ptr(), rp.height * rp.width, rgb.data_ptr(), stream.cuda_stream)
             film = rgb
         if not to_host:
             return film, stats
-        hf, hs = film.cpu().numpy(), stats.cpu().numpy()
+        hf, hs = _to_pinned(dev_scene, film), stats.cpu().numpy()
     return hf, dict(paths=int(hs[0]), segments=int(hs[1]), rays=int(hs[2]), shadow_rays=int(hs[3]))

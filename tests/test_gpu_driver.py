@@ -92,6 +92,32 @@ def test_pulse_shape_matches_oracle():
     assert np.abs(lhs - rhs).max() <= 1e-4 * np.abs(lhs).max()
 
 
+def test_sharded_entry_points_single_rank():
+    """distributed.acquire_sharded / render_sharded without a process group (world size 1) == the plain calls; the
+    multi-rank arithmetic (shard_samples + one sum all-reduce) is covered by the gloo test and by sharded == unsharded."""
+    torch = pytest.importorskip("torch")
+    from prt_b200 import mi_compat as mi
+    from prt_b200.distributed import acquire_sharded, render_sharded
+    from prt_b200.scene import AcqParams
+    desc = scenes.ultrasound_scene("Plate_Box", "intended")
+    scene = mi.Scene(desc)
+    p = AcqParams.from_props(desc.integrator, desc.sensor)
+    dev = scene.device()
+    ref, rtx, rst = dev.acquire(p, seed=3, spp=64)
+    for _ in range(2):          # second call reuses the cached device tensors
+        got, tx, st = acquire_sharded(dev, p, seed=3, spp_total=64)
+        assert st["paths"] == rst["paths"] and st["segments"] == rst["segments"] and st["deposits"] == rst["deposits"]
+        assert np.allclose(tx, rtx) and np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    d_buf, _, d_st = acquire_sharded(dev, p, seed=3, spp_total=64, to_host=False)
+    assert d_buf.is_cuda and int(d_st[0]) == rst["paths"]
+    cb = mi.Scene(scenes.cbox_scene(48, 8))
+    rp = cb.integrator().render_params(cb)
+    img, ist = cb.device().render_image(rp, seed=5, spp=8)
+    got, gst = render_sharded(cb.device(), rp, seed=5, spp_total=8, develop=True)
+    assert gst["rays"] == ist["rays"] and got.shape == (48, 48, 3)
+    assert np.allclose(got, img, rtol=2e-4, atol=1e-6)
+
+
 def test_usmain_call_sequence():
     """What USMain.py does, with 2 optimisation iterations instead of 25 and 64 samples per element so that the
     finite-difference loss is not pure noise."""

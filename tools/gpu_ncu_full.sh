@@ -13,7 +13,7 @@ run hf_closest k_wf_trace 4 python tools/prof_render.py --workload heightfield -
 run hf_shadow k_wf_trace 5 python tools/prof_render.py --workload heightfield --res 3840 --spp 2 --launches 1
 run hf_shade 'k_wf_shade' 2 python tools/prof_render.py --workload heightfield --res 3840 --spp 2 --launches 1
 run cbox_closest k_wf_trace 2 python tools/prof_render.py --workload cbox --res 2048 --spp 4 --launches 1
-run cbox_shade 'k_wf_shade' 1 python tools/prof_render.py --workload cbox --res 2048 --spp 4 --launches 1
+run cbox_shade 'k_wf_shade' 3 python tools/prof_render.py --workload cbox --res 2048 --spp 4 --launches 1
 run sphere_box k_acquire 2 python tools/prof_acquire.py --workload sphere_box --launches 1
 run ring k_acquire 2 python tools/prof_acquire.py --workload ring --launches 1
 ls -la gpurun_out/*.ncu-rep
