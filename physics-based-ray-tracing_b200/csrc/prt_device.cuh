@@ -204,14 +204,22 @@ __device__ __forceinline__ float intersect_prim(const DPrim &pr, float3 o, float
         if (n0 < 0.0f && n1 > tmax) return -1.0f;
         return n0 < 0.0f ? n1 : n0;
     }
-    float3 ol = xpoint(pr.o0, pr.o1, pr.o2, o), dl = xvec(pr.o0, pr.o1, pr.o2, d);
     if (pr.kind == 1 || pr.kind == 3) {  // rectangle / disk
-        float t = -ol.z / dl.z;
+        // object-space z row first: most candidates are rejected on t alone, before the x / y rows are transformed
+        // (same operations in the same order as xpoint / xvec, so t, lx, ly are bit-identical to the full transform)
+        const float olz = fmaf(pr.o2.x, o.x, fmaf(pr.o2.y, o.y, fmaf(pr.o2.z, o.z, pr.o2.w)));
+        const float dlz = fmaf(pr.o2.x, d.x, fmaf(pr.o2.y, d.y, pr.o2.z * d.z));
+        float t = -olz / dlz;
         if (!(t >= 0.0f && t <= tmax)) return -1.0f;
-        float lx = fmaf(t, dl.x, ol.x), ly = fmaf(t, dl.y, ol.y);
+        const float olx = fmaf(pr.o0.x, o.x, fmaf(pr.o0.y, o.y, fmaf(pr.o0.z, o.z, pr.o0.w)));
+        const float oly = fmaf(pr.o1.x, o.x, fmaf(pr.o1.y, o.y, fmaf(pr.o1.z, o.z, pr.o1.w)));
+        const float dlx = fmaf(pr.o0.x, d.x, fmaf(pr.o0.y, d.y, pr.o0.z * d.z));
+        const float dly = fmaf(pr.o1.x, d.x, fmaf(pr.o1.y, d.y, pr.o1.z * d.z));
+        float lx = fmaf(t, dlx, olx), ly = fmaf(t, dly, oly);
         bool in = pr.kind == 1 ? (fabsf(lx) <= 1.0f && fabsf(ly) <= 1.0f) : (lx * lx + ly * ly <= 1.0f);
         return in ? t : -1.0f;
     }
+    float3 ol = xpoint(pr.o0, pr.o1, pr.o2, o), dl = xvec(pr.o0, pr.o1, pr.o2, d);
     float A, B, C;
     if (pr.kind == 2) {  // cone x^2+y^2 = (1-z)^2
         float w = 1.0f - ol.z;

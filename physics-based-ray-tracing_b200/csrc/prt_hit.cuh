@@ -97,9 +97,11 @@ __device__ __forceinline__ bool closest_hit(const DScene &sc, const DPrim *prims
 
 template <bool TRIS = true>
 __device__ __forceinline__ bool occluded(const DScene &sc, const DPrim *prims, float3 o, float3 d, float tmax) {
-    bool hit = false;
-    for (int i = 0; i < sc.n_prims; i++) hit |= intersect_prim(prims[i], o, d, tmax) >= 0.0f;
-    if (hit || !TRIS) return hit;
+    // any hit: leave at the first one (in the Box scenes the connection ray of a whole warp is blocked by the same
+    // primitive, so the exit is warp-uniform)
+    for (int i = 0; i < sc.n_prims; i++)
+        if (intersect_prim(prims[i], o, d, tmax) >= 0.0f) return true;
+    if (!TRIS) return false;
     float b1, b2, tt = tmax;
     return traverse_tris<true>(sc, o, d, tt, b1, b2) >= 0;
 }
