@@ -49,8 +49,10 @@ struct PathState {
 
 __device__ __forceinline__ float elem_x(const AcqDev &P, int e) { return P.pitch * ((float) e - (float) (P.n_e - 1) * 0.5f); }  // CI:84
 
-__device__ __forceinline__ void init_path(const AcqDev &P, uint64_t ae, uint32_t s, PathState &ps) {
-    int a = (int) (ae / (uint64_t) P.n_e), e = (int) (ae % (uint64_t) P.n_e);
+__device__ __forceinline__ void init_path(const AcqDev &P, uint32_t ae, uint32_t s, PathState &ps) {
+    // n_a * n_e fits 32 bits (fill_params): 32-bit division, not the 64-bit call
+    const uint32_t qa = ae / (uint32_t) P.n_e;
+    int a = (int) qa, e = (int) (ae - qa * (uint32_t) P.n_e);
     float2 sc = __ldg(P.sincos + a);
     float xe = elem_x(P, e);
     ps.t0 = (xe * sc.x) / P.c;                                                  // CI:87
@@ -58,7 +60,7 @@ __device__ __forceinline__ void init_path(const AcqDev &P, uint64_t ae, uint32_t
     ps.d = normalize(xvec(P.T0, P.T1, P.T2, mk3(sc.x, 0.0f, sc.y)));            // CI:98,104
     ps.amp = 1.0f; ps.atten = 1.0f; ps.tof = 0.0f; ps.geo = 0.0f;               // CI:110-114
     ps.a = a; ps.depth = 0;
-    ps.rng = path_rng(P.seed, ae * (uint64_t) P.spp_total + (uint64_t) s);      // RNG contract, SURVEY.md 8(d)
+    ps.rng = path_rng(P.seed, (uint64_t) ae * (uint64_t) P.spp_total + (uint64_t) s);      // RNG contract, SURVEY.md 8(d)
 }
 
 struct Counters {
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const Acq
     for (;;) {
         if (!live) {
             if (si >= P.n_s) break;
-            init_path(P, (uint64_t) (ae0 + ae), P.s_offset + (uint32_t) si * P.s_stride, ps);
+            init_path(P, ae0 + ae, P.s_offset + (uint32_t) si * P.s_stride, ps);
             ae += d_ae;
             si += d_si;
             if (ae >= n_ae) { ae -= n_ae; si++; }
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire_trace(const AcqDev P, c
     uint64_t path = path_idx[i];
     PathState ps;
     Counters cn = { 0, 0, 0, 0, 0 };
-    init_path(P, path / P.spp_total, (uint32_t) (path % P.spp_total), ps);
+    init_path(P, (uint32_t) (path / P.spp_total), (uint32_t) (path % P.spp_total), ps);
     bool live = P.max_depth > 0;
     while (live) live = segment<true>(P, prims, ps, cn, rec + i * (uint64_t) P.max_depth);
 }
@@ -226,6 +228,7 @@ static int fill_params(prt_scene *s, const prt_acq_params *p, uint64_t seed, uin
                 "acquire: invalid acquisition parameters");
     PRT_REQUIRE(spp_total > 0, "acquire: spp_total must be > 0");
     PRT_REQUIRE((uint64_t) p->n_angles * p->n_elements * (uint64_t) p->time_samples < (1ull << 40), "acquire: channel buffer too large");
+    PRT_REQUIRE((uint64_t) p->n_angles * p->n_elements < (1ull << 31), "acquire: more than 2^31 (angle, element) pairs");
     prt_context *c = s->ctx;
     int rc = ensure_scratch(c, 0, 0, (size_t) p->n_angles);
     if (rc) return rc;

@@ -54,6 +54,9 @@ struct prt_context {
     void     *pinned;    size_t pinned_cap;   // pinned staging for D2H of results
     void     *wf_dev = nullptr; size_t wf_cap = 0;   // wavefront path-tracer state / queues (prt_wavefront.cu)
     int       last_launches = 0;              // kernels enqueued by the most recent render call
+    // grow-only device scratch slots for the post-processing entry points (prt_das.cu): no cudaMalloc / cudaFree (and the
+    // device-wide synchronisation cudaFree implies) per call
+    struct Scratch { void *p = nullptr; size_t cap = 0; } scratch[8];
     // optional per-kernel-class timing (prt_profile_begin / prt_profile_read): CUDA event pairs on the launching stream
     bool prof_on = false;
     struct ProfPair { int cls, kernels; cudaEvent_t e0, e1; };
@@ -126,4 +129,5 @@ int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, cons
                float4 **out_nodes8, uint32_t *out_n_nodes8, float4 **out_tri_v8, uint32_t **out_tri8_sorted, int *out_levels,
                cudaStream_t st);
 int ensure_scratch(prt_context *ctx, size_t acc_floats, size_t aux_floats, size_t n_angles);
+int scratch_slot(prt_context *ctx, int slot, size_t bytes, void **out);   // grow-only; contents undefined after growth
 }  // namespace prt

@@ -39,6 +39,19 @@ static bool invert_affine(const double m[16], double inv[12]) {
     return true;
 }
 
+int scratch_slot(prt_context *ctx, int slot, size_t bytes, void **out) {
+    prt_context::Scratch &s = ctx->scratch[slot];
+    if (bytes > s.cap) {
+        if (s.p) cudaFree(s.p);
+        s.p = nullptr;
+        s.cap = 0;
+        PRT_CUDA(cudaMalloc(&s.p, bytes));
+        s.cap = bytes;
+    }
+    *out = s.p;
+    return PRT_OK;
+}
+
 int ensure_scratch(prt_context *ctx, size_t acc_floats, size_t aux_floats, size_t n_angles) {
     if (acc_floats > ctx->acc_cap) {
         if (ctx->acc_dev) cudaFree(ctx->acc_dev);
@@ -152,6 +165,8 @@ int prt_destroy(prt_context *c) {
     if (c->stats_dev) cudaFree(c->stats_dev);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->wf_dev) cudaFree(c->wf_dev);
+    for (auto &sl : c->scratch)
+        if (sl.p) cudaFree(sl.p);
     for (auto &pp : c->prof) { cudaEventDestroy(pp.e0); cudaEventDestroy(pp.e1); }
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);

@@ -261,8 +261,8 @@ def das_beamform(channel, angles_deg, x, z, fs, sound_speed, pitch, t0=0.0, f_nu
         raise ValueError("das_beamform: one angle per transmission expected")
     p = capi.DasParamsC(n_a, n_e, T, xs.size, zs.size, float(fs), float(sound_speed), float(pitch), float(t0), float(f_number))
     txd = None if tx_delays is None else np.ascontiguousarray(tx_delays, dtype=np.float32)
-    rf = np.empty((xs.size, zs.size), dtype=np.float32)
-    env = np.empty((xs.size, zs.size), dtype=np.float32)
+    rf = ctx.pinned_array((xs.size, zs.size), np.float32)      # page-locked: the two D2H copies need no staging
+    env = ctx.pinned_array((xs.size, zs.size), np.float32)
     check(ctx.L.prt_das_beamform(ctx.h, C.byref(p), fptr(ch), fptr(txd), dptr(ang), fptr(xs), fptr(zs), fptr(rf), fptr(env)),
           "prt_das_beamform")
     return rf, env
@@ -287,6 +287,6 @@ def pulse_shape(channel, fs, fc, sigma_s=None, wave_cycles=None, context: Option
     ch = np.ascontiguousarray(channel, dtype=np.float32)
     T = ch.shape[-1]
     rows = ch.size // T
-    out = np.empty_like(ch)
+    out = ctx.pinned_array(ch.shape, np.float32)
     check(ctx.L.prt_pulse_shape(ctx.h, fptr(ch), rows, T, float(fs), float(fc), float(sigma_s), fptr(out)), "prt_pulse_shape")
     return out
