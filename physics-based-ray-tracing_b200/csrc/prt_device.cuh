@@ -346,6 +346,67 @@ __device__ __forceinline__ bool intersect_tri_wt(const RayPre &rp, float3 o, flo
     return true;
 }
 
+// The same test with the permutation folded into three matrix rows per ray:
+//   rx = e_kx - Sx e_kz,  ry = e_ky - Sy e_kz,  rz = Sz e_kz          (entries 1, 0 and the shear constant)
+// so that (Ax, Ay, Az) = (A.rx, A.ry, A.rz) needs no run-time component selection.  comp() costs two compares and two
+// selects per use; nine uses per triangle were 13-15 % of all instructions of the mesh kernels (profiles/r01, ncu joined
+// with line info).  Products with 0 and 1 are exact, so each row dot differs from Woop's single fused multiply-add by at
+// most one extra rounding -- and it is still a function of (vertex, ray) only: a vertex shared by two triangles maps to
+// the same point, which is all watertightness needs.  The edge functions stay un-fused.
+struct RayRows {
+    float3 rx, ry, rz;
+};
+
+__device__ __forceinline__ RayRows ray_rows(const RayPre &p) {
+    RayRows r;
+    r.rx = mk3((p.kx == 0 ? 1.0f : 0.0f) - (p.kz == 0 ? p.Sx : 0.0f), (p.kx == 1 ? 1.0f : 0.0f) - (p.kz == 1 ? p.Sx : 0.0f),
+               (p.kx == 2 ? 1.0f : 0.0f) - (p.kz == 2 ? p.Sx : 0.0f));
+    r.ry = mk3((p.ky == 0 ? 1.0f : 0.0f) - (p.kz == 0 ? p.Sy : 0.0f), (p.ky == 1 ? 1.0f : 0.0f) - (p.kz == 1 ? p.Sy : 0.0f),
+               (p.ky == 2 ? 1.0f : 0.0f) - (p.kz == 2 ? p.Sy : 0.0f));
+    r.rz = mk3(p.kz == 0 ? p.Sz : 0.0f, p.kz == 1 ? p.Sz : 0.0f, p.kz == 2 ? p.Sz : 0.0f);
+    return r;
+}
+
+__device__ __forceinline__ float row_dot(float3 v, float3 r) { return fmaf(v.x, r.x, fmaf(v.y, r.y, v.z * r.z)); }
+
+__device__ __forceinline__ bool intersect_tri_rows(const RayRows &rr, float3 o, float3 v0, float3 v1, float3 v2, float &tbest,
+                                                   float &b1, float &b2) {
+    const float3 A = v0 - o, B = v1 - o, C = v2 - o;
+    const float Ax = row_dot(A, rr.rx), Ay = row_dot(A, rr.ry);
+    const float Bx = row_dot(B, rr.rx), By = row_dot(B, rr.ry);
+    const float Cx = row_dot(C, rr.rx), Cy = row_dot(C, rr.ry);
+    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {  // exactly on an edge: decide in double
+        double CxBy = (double) Cx * (double) By, CyBx = (double) Cy * (double) Bx;
+        U = (float) (CxBy - CyBx);
+        double AxCy = (double) Ax * (double) Cy, AyCx = (double) Ay * (double) Cx;
+        V = (float) (AxCy - AyCx);
+        double BxAy = (double) Bx * (double) Ay, ByAx = (double) By * (double) Ax;
+        W = (float) (BxAy - ByAx);
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = U + V + W;
+    if (det == 0.0f) return false;
+    const float Az = row_dot(A, rr.rz), Bz = row_dot(B, rr.rz), Cz = row_dot(C, rr.rz);
+    const float T = fmaf(U, Az, fmaf(V, Bz, W * Cz));
+    const float rdet = 1.0f / det;
+    const float t = T * rdet;
+    if (!(t >= 0.0f && t <= tbest)) return false;
+    tbest = t;
+    b1 = V * rdet;
+    b2 = W * rdet;
+    return true;
+}
+
+#ifndef PRT_TRI_ROWS
+#define PRT_TRI_ROWS 1      // 1: intersect_tri_rows in every traversal; 0: the component-selecting intersect_tri_wt (A/B)
+#endif
+#ifndef PRT_ROWS_LATE
+#define PRT_ROWS_LATE 0     // binary traversal: 1 rebuilds the rows at every leaf, 0 keeps them in registers across the node loop
+#endif
+
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 
 // slab test against one child box; returns entry distance or +inf on a miss
@@ -368,6 +429,9 @@ template <bool ANY>
 __device__ __forceinline__ int traverse_bvh(const DScene &sc, float3 o, float3 d, float &tbest, float &b1, float &b2) {
     if (sc.n_tris == 0) return -1;
     const RayPre rp = ray_precompute(d);
+#if PRT_TRI_ROWS && !PRT_ROWS_LATE
+    const RayRows rr = ray_rows(rp);
+#endif
     const float3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     int   stack_ref[PRT_STACK];
     float stack_t[PRT_STACK];
@@ -411,10 +475,17 @@ __device__ __forceinline__ int traverse_bvh(const DScene &sc, float3 o, float3 d
         {
             int code = ~ref;
             int first = code >> 2, count = (code & 3) + 1;
+#if PRT_TRI_ROWS && PRT_ROWS_LATE
+            const RayRows rr = ray_rows(rp);     // rebuilt per leaf instead of living through the node loop
+#endif
             for (int j = 0; j < count; j++) {
                 const float4 *tv = sc.tri_v + 3 * (size_t) (first + j);
                 float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
+#if PRT_TRI_ROWS
+                if (intersect_tri_rows(rr, o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#else
                 if (intersect_tri_wt(rp, o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#endif
                     best = first + j;
                     if (ANY) return best;
                 }

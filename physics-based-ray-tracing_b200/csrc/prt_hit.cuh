@@ -23,6 +23,9 @@ template <bool ANY>
 __device__ __forceinline__ int traverse_bvh8(const DScene &sc, float3 o, float3 d, float &tbest, float &b1, float &b2) {
     if (sc.n_tris == 0) return -1;
     const RayPre rp = ray_precompute(d);
+#if PRT_TRI_ROWS
+    const RayRows rr = ray_rows(rp);
+#endif
     const Bvh8Ray r8 = bvh8_ray(o, d);
     uint2 gstack[BVH8_STACK];
     int sp = 0, best = -1;
@@ -46,7 +49,11 @@ __device__ __forceinline__ int traverse_bvh8(const DScene &sc, float3 o, float3 
             tg.y &= ~(1u << bit);
             const float4 *tv = sc.tri_v8 + 3 * (size_t) (tg.x + (uint32_t) bit);
             const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
+#if PRT_TRI_ROWS
+            if (intersect_tri_rows(rr, o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#else
             if (intersect_tri_wt(rp, o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#endif
                 best = (int) (__float_as_uint(b.w) >> 2);      // k_bvh8_annotate: (sorted triangle << 2) | shading queue
                 if (ANY) return best;
             }

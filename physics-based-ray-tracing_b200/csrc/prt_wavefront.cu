@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
     RayPre rp;
     rp.kx = 0; rp.ky = 1; rp.kz = 2; rp.Sx = rp.Sy = 0.0f; rp.Sz = 1.0f;
     int kpack = 0;
+
     float tbest = 0.0f, b1 = 0.0f, b2 = 0.0f, prim_t = 0.0f;
     int best = -1, best_prim = -1, sp = 0;      // best: (sorted triangle << 2) | shading queue, or -1
     uint2 ng = make_uint2(0, 0);                // node group in hand: child base, hit bits | imask
@@ -418,13 +419,23 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
         // ---- the triangles those nodes yielded ----
         const unsigned mT = __ballot_sync(FULL, tg.y != 0u);
         if (__popc(mT) > WF_COOP_MAX) {
-            // most lanes hold triangles (small scenes, coherent rays): every lane walks its own list
+            // most lanes hold triangles (small scenes, coherent rays): every lane walks its own list.  The shear rows of
+            // the selection-free triangle test (intersect_tri_rows) are rebuilt here, once per list, rather than carried
+            // through the traversal loop: nine more live registers spill at 64 (height field 1 875 -> 1 818 Mrays/s), and
+            // the cooperative branch below would have to shuffle nine values per pair instead of four
+#if PRT_TRI_ROWS
+            const RayRows rr = ray_rows(rp);
+#endif
             while (tg.y) {
                 const int bit = 31 - __clz(tg.y);
                 tg.y &= ~(1u << bit);
                 const float4 *tv = sc.tri_v8 + 3 * (size_t) (tg.x + (uint32_t) bit);
                 const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
+#if PRT_TRI_ROWS
+                if (intersect_tri_rows(rr, r8.o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#else
                 if (intersect_tri_wt(rp, r8.o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#endif
                     best = __float_as_int(b.w);
                     if (ANY) { busy = false; break; }
                 }
@@ -470,7 +481,13 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                     for (unsigned r = p - o_off; r; r--) m &= m - 1u;
                     const float4 *tv = sc.tri_v8 + 3 * (size_t) (o_base + (uint32_t) (__ffs(m) - 1));
                     const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
+#if PRT_TRI_ROWS
+                    // same arithmetic as the per-lane branch and the megakernels (bit-identical hits across back ends);
+                    // the rows are rebuilt from the four shuffled words rather than shuffled as nine
+                    hit = intersect_tri_rows(ray_rows(q), ro, xyz(a), xyz(b), xyz(c), ht, hb1, hb2);
+#else
                     hit = intersect_tri_wt(q, ro, xyz(a), xyz(b), xyz(c), ht, hb1, hb2);
+#endif
                     hid = __float_as_int(b.w);
                     ht += 0.0f;
                     if (hit) atomicMin(&stm[own], __float_as_uint(ht));
