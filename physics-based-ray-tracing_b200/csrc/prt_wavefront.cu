@@ -68,7 +68,10 @@ static constexpr int WF_SHADE_THREADS = 256;
 #endif
 static_assert(WF_QCHUNK == 0 || WF_QCHUNK >= 32, "a retire event appends up to 32 entries: one fresh chunk must hold them");
 static constexpr uint32_t WF_HOLE = 0xffffffffu;   // unused tail of a warp's reserved queue chunk
-enum { C_EXT = 0, C_MAT = 1, C_SH = 4, C_HEAD_EXT = 8, C_HEAD_SH = 12 };
+// per-bounce counter block.  C_SH is the LAST int of a block and C_EXT the first of the next one, and the array starts one
+// int past an 8-byte boundary: the shadow-ray count of bounce b and the extend-ray count of bounce b + 1 form one aligned
+// 64-bit word, so a shading warp reserves both of its output ranges with a single atomic.
+enum { C_EXT = 0, C_MAT = 1, C_HEAD_EXT = 8, C_HEAD_SH = 12, C_SH = WF_CSTRIDE - 1 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -535,7 +538,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
 template <int QI>
 __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(const PtDev P, const WfBuf B, const int bounce) {
     int *C = B.cnt + bounce * WF_CSTRIDE;
-    int *Cn = C + WF_CSTRIDE;
+    static_assert(C_SH + 1 == WF_CSTRIDE && C_EXT == 0, "shadow count of bounce b must sit right below the extend count of bounce b + 1");
     // Two ways to find this kernel's paths.  The compacted queue (slot ids appended by the trace kernel, ballot +
     // prefix popcount per retire event) costs nothing for sparse materials, but it is filled in RETIRE order, which
     // drifts towards a random permutation of the slots within ~5 bounces: path state is then gathered from scattered
@@ -583,12 +586,22 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(co
             if (!live) B.tag[slot] = 0;      // a live path's tag is rewritten when its next ray retires
 #endif
         }
-        const int j = wf_reserve(C + C_SH, sr.want);
+        // one 64-bit atomic per warp for both output queues (two dependent round trips to L2 were 18 % of this kernel's
+        // stall samples at its 25 % occupancy)
+        const unsigned m_sh = __ballot_sync(FULL, sr.want), m_ex = __ballot_sync(FULL, live);
+        unsigned long long base2 = 0ull;
+        if (m_sh | m_ex) {
+            if ((threadIdx.x & 31) == 0)
+                base2 = atomicAdd(reinterpret_cast<unsigned long long *>(C + C_SH),
+                                  (unsigned long long) __popc(m_sh) | ((unsigned long long) __popc(m_ex) << 32));
+            base2 = __shfl_sync(FULL, base2, 0);
+        }
+        const int j = (int) (base2 & 0xffffffffull) + __popc(m_sh & lanemask_lt());
+        const int e = (int) (base2 >> 32) + __popc(m_ex & lanemask_lt());
         if (sr.want) {
             wf_write_ray(B.sh, j, sr.o, sr.d, sr.tmax, slot, sr.w);
             B.SHC[j] = make_float4(sr.c.x, sr.c.y, sr.c.z, 0.0f);
         }
-        const int e = wf_reserve(Cn + C_EXT, live);
         if (live) wf_write_ray(Rn, e, st.o, st.d, PRT_INF, slot, 0.0f);
     }
 }
@@ -640,7 +653,7 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
     const uint64_t cap = layers * L;
     PRT_REQUIRE(cap < (1ull << 31), "render_path (wavefront): batch too large");
     const int bounces = P.max_depth > 1 ? P.max_depth : 1;
-    const size_t cnt_bytes = (sizeof(int) * WF_CSTRIDE * (size_t) (bounces + 1) + 255) & ~(size_t) 255;
+    const size_t cnt_bytes = (sizeof(int) * (WF_CSTRIDE * (size_t) (bounces + 1) + 2) + 255) & ~(size_t) 255;
     const size_t per_slot = 16 * (8 + 8 + 4 + 1) + 4 * WF_QUEUES;
     // every trace warp may leave one partly used chunk per queue behind (holes): room for them on top of `cap` entries
     const size_t q_slack = (size_t) c->sm_count * 64 * (WF_QCHUNK ? WF_QCHUNK : 1);
@@ -657,7 +670,7 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
         char *p = reinterpret_cast<char *>(c->wf_dev);
         auto take = [&](size_t bytes) { char *r = p; p += bytes; return r; };
         auto take4 = [&]() { return reinterpret_cast<float4 *>(take(16 * cap)); };
-        B.cnt = reinterpret_cast<int *>(take(cnt_bytes));
+        B.cnt = reinterpret_cast<int *>(take(cnt_bytes)) + 1;      // odd int offset: see the counter layout above
         B.ST = reinterpret_cast<float4 *>(take(128 * cap));
         for (int k = 0; k < 2; k++) { B.ext[k].r0 = take4(); B.ext[k].r1 = take4(); B.ext[k].r2 = take4(); B.ext[k].r3 = take4(); }
         B.sh.r0 = take4(); B.sh.r1 = take4(); B.sh.r2 = take4(); B.sh.r3 = take4();
@@ -680,7 +693,7 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
     for (uint64_t j0 = 0; j0 < P.n_s; j0 += layers) {
         B.j0 = (uint32_t) j0;
         B.n_layers = (uint32_t) (P.n_s - j0 < layers ? P.n_s - j0 : layers);
-        PRT_CUDA(cudaMemsetAsync(B.cnt, 0, cnt_bytes, st));
+        PRT_CUDA(cudaMemsetAsync(B.cnt - 1, 0, cnt_bytes, st));
 #if WF_SLOT_SHADE
         PRT_CUDA(cudaMemsetAsync(B.tag, 0, (size_t) B.n_layers * L, st));
 #endif
