@@ -219,6 +219,34 @@ def cbox_scene(res: int = 256, spp: int = 128, max_depth: int = 6) -> SceneDesc:
     return desc
 
 
+def furnace_scene_dict(res: int = 16, spp: int = 64, max_depth: int = 6, rho: float = 0.5, rr_depth: int = 1000) -> dict:
+    """Closed-form anchor for the `path` integrator (row a14): a closed box whose six walls all emit radiance 1 and
+    reflect diffusely with albedo rho, camera inside.  Every pixel is exactly sum_{i < max_depth} rho^i in expectation
+    (emission seen after 0 .. max_depth-1 bounces; Mitsuba's depth convention), whatever mix of
+    emitter sampling, BSDF sampling, MIS weights and Russian roulette the estimator uses."""
+    d = {"type": "scene", "integrator": {"type": "path", "max_depth": max_depth, "rr_depth": rr_depth},
+         "sensor": {"type": "perspective", "fov_axis": "smaller", "near_clip": 0.001, "far_clip": 100.0, "fov": 60.0,
+                    "to_world": T().look_at([0.1, 0.2, 0.3], [0.5, -0.4, -1], [0, 1, 0]),
+                    "sampler": {"type": "independent", "sample_count": spp},
+                    "film": {"type": "hdrfilm", "width": res, "height": res, "rfilter": {"type": "tent"}}},
+         "wall": {"type": "diffuse", "reflectance": [rho, rho, rho]}}
+    quads = {"floor": [(-1, -1, 1), (1, -1, 1), (1, -1, -1), (-1, -1, -1)], "ceiling": [(1, 1, -1), (1, 1, 1), (-1, 1, 1), (-1, 1, -1)],
+             "back": [(1, -1, -1), (1, 1, -1), (-1, 1, -1), (-1, -1, -1)], "front": [(-1, -1, 1), (-1, 1, 1), (1, 1, 1), (1, -1, 1)],
+             "left": [(-1, 1, -1), (-1, 1, 1), (-1, -1, 1), (-1, -1, -1)], "right": [(1, -1, 1), (1, 1, 1), (1, 1, -1), (1, -1, -1)]}
+    for k, pts in quads.items():
+        q = _quad(pts)
+        q["bsdf"] = {"type": "ref", "id": "wall"}
+        q["emitter"] = {"type": "area", "radiance": [1.0, 1.0, 1.0]}
+        d[k] = q
+    return d
+
+
+def furnace_scene(res: int = 16, spp: int = 64, max_depth: int = 6, rho: float = 0.5, rr_depth: int = 1000) -> SceneDesc:
+    desc = load_dict_desc(furnace_scene_dict(res, spp, max_depth, rho, rr_depth))
+    desc.source = "<builtin:furnace>"
+    return desc
+
+
 def heightfield_scene_dict(n: int = 2237, res=(3840, 2160), spp: int = 64) -> dict:
     """BASELINE.json config 5: closed box x,z in [-1,1], y in [-1.2,1], ceiling light quad,
     floor = height field of 2 (n-1)^2 triangles (n = 2237 -> 9 999 392) around y = -1, all diffuse 0.5, exactly

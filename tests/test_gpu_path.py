@@ -60,6 +60,25 @@ def test_directly_visible_emitter_is_exact():
     assert np.allclose(img[8:-8, 8:-8], 1.0, atol=1e-5)
 
 
+@pytest.mark.parametrize("max_depth,rho,rr_depth", [(1, 0.5, 1000), (2, 0.5, 1000), (6, 0.5, 1000), (6, 0.8, 2), (12, 0.3, 3)])
+def test_furnace_closed_form(max_depth, rho, rr_depth, monkeypatch):
+    """Both GPU back ends against the closed form sum_{i < max_depth} rho^i of the all-emitting closed box
+    (scenes.furnace_scene): pins emitter hits + MIS, NEE, BSDF sampling and Russian roulette without any reference."""
+    desc = scenes.furnace_scene(32, 256, max_depth, rho, rr_depth)
+    scene = mi.Scene(desc)
+    rp = scene.integrator().render_params(scene)
+    expect = sum(rho ** i for i in range(max_depth))
+    for mode in ("wavefront", "mega"):
+        film, st = _render_mode(scene.device(), rp, mode, monkeypatch, seed=3, spp=256)
+        img = _image(film)
+        assert st["rays"] - st["shadow_rays"] == st["segments"]           # closed box: nothing escapes
+        if max_depth == 1:
+            assert np.allclose(img, 1.0, atol=1e-6)
+        else:
+            assert abs(img.mean() - expect) <= 1.5e-3 * expect, (mode, img.mean(), expect)
+            assert np.abs(img - expect).max() <= 0.12 * expect                # every pixel, 256 spp
+
+
 def test_render_sharded_equals_unsharded():
     desc = scenes.cbox_scene(48, 32)
     scene = mi.Scene(desc)

@@ -236,6 +236,27 @@ def test_c_oracle_equals_python_transliteration(orc, name, order):
     assert np.allclose(buf_c, buf_p, rtol=1e-6, atol=1e-15)
 
 
+@pytest.mark.parametrize("max_depth,rho,rr_depth", [(1, 0.5, 1000), (2, 0.5, 1000), (6, 0.5, 1000), (6, 0.8, 2), (12, 0.3, 3)])
+def test_path_tracer_oracle_furnace_closed_form(max_depth, rho, rr_depth):
+    """Closed-form pin of oracle/orc_pt.inl (row a14 has no reference code): in a closed box whose walls all emit 1 and
+    reflect with albedo rho, every pixel is sum_{i < max_depth} rho^i -- emitter sampling, BSDF sampling, MIS and Russian
+    roulette must cancel to exactly that.  max_depth = 1 is exact (emission only); the others are Monte-Carlo means."""
+    import orc_py
+    from prt_b200 import mi_compat as mi
+    desc = scenes.furnace_scene(16, 64, max_depth, rho, rr_depth)
+    sc = mi.Scene(desc)
+    rp = sc.integrator().render_params(sc)
+    film, st = orc_py.render_path(orc_py.OracleScene(desc), rp, seed=1, spp=64, prec=32)
+    img = film[..., :3] / film[..., 3:]
+    expect = sum(rho ** i for i in range(max_depth))
+    assert st["misses"] == 0
+    if max_depth == 1:
+        assert np.allclose(img, 1.0, atol=1e-6)
+    else:
+        assert abs(img.mean() - expect) <= 4e-3 * expect, (img.mean(), expect)
+        assert np.abs(img.mean((0, 1)) - expect).max() <= 6e-3 * expect          # per channel
+
+
 def test_pulse_shape_oracle_equals_the_prototype_echo_sum():
     """oracle/pyref.pulse_shape (checker of the f4 kernel) against the literal per-echo sum of RayTracingV0.py:193-201."""
     import pyref
