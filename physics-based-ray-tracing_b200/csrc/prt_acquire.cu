@@ -161,10 +161,26 @@ __device__ __forceinline__ const DPrim *stage_prims(const DScene &sc, DPrim *sme
 
 // occupancy targets: the analytic-only specialisation has no traversal stack and fits 4 CTAs/SM (64 regs);
 // the BVH one is held at 3 CTAs/SM (80 regs)
-template <bool TRIS>
+// GPRIMS = true: more than MAX_SMEM_PRIMS analytic primitives, read from global memory.  Making that a template
+// parameter (instead of a run-time pointer choice) lets the compiler see that `prims` points into shared memory in the
+// common case and emit LDS instead of generic loads.
+#ifndef PRT_ACQ_LDS
+#define PRT_ACQ_LDS 1
+#endif
+template <bool TRIS, bool GPRIMS>
 __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const AcqDev P) {
     __shared__ DPrim sprims[MAX_SMEM_PRIMS];
+#if PRT_ACQ_LDS
+    const DPrim *prims = GPRIMS ? P.sc.prims : sprims;
+    if (!GPRIMS) {
+        const float4 *src = reinterpret_cast<const float4 *>(P.sc.prims);
+        float4 *dst = reinterpret_cast<float4 *>(sprims);
+        for (int i = threadIdx.x; i < P.sc.n_prims * (int) (sizeof(DPrim) / 16); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+#else
     const DPrim *prims = stage_prims(P.sc, sprims);
+#endif
     // sample-major launch order: consecutive lanes -> consecutive (angle, element) of this launch's angle range,
     // same sample.  (ae, si) advance incrementally -- no 64-bit divisions in the loop.
     const uint32_t n_ae = (uint32_t) P.a_count * (uint32_t) P.n_e;
@@ -287,8 +303,10 @@ static int launch_acquire(prt_context *c, const AcqDev &P, cudaStream_t st) {
     // persistent grid: a whole number of CTAs per SM (occupancy-derived), never more than the work needs
     const bool tris = P.sc.n_tris > 0;
     int per_sm = 0;
-    if (tris) PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acquire<true>, ACQ_THREADS, 0));
-    else PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acquire<false>, ACQ_THREADS, 0));
+    const bool gp = P.sc.n_prims > MAX_SMEM_PRIMS;
+    void (*kern)(const AcqDev) = tris ? (gp ? k_acquire<true, true> : k_acquire<true, false>)
+                                      : (gp ? k_acquire<false, true> : k_acquire<false, false>);
+    PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACQ_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     const uint64_t n_ae_l = (uint64_t) P.a_count * P.n_e;
     uint64_t want = (P.n_s * n_ae_l + ACQ_THREADS - 1) / ACQ_THREADS;
@@ -299,8 +317,7 @@ static int launch_acquire(prt_context *c, const AcqDev &P, cudaStream_t st) {
     if (grid < 1) grid = 1;
     {
         ProfScope ps(c, PRT_KC_ACQUIRE, st);
-        if (tris) k_acquire<true><<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
-        else k_acquire<false><<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
+        kern<<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
     }
     PRT_CUDA(cudaGetLastError());
     return PRT_OK;
