@@ -110,17 +110,6 @@ __device__ __forceinline__ bool segment(const AcqDev &P, const DPrim *prims, Pat
     ultra_bsdf_sample(wi, h.ng, h.ns, mZ, mA, s1, s2, dir, pdf, a_resp, reflect);   // CI:175 / 338
     const float cos_theta = dot(h.ns, md);                                       // CI:176 / 340
     ps.amp *= a_resp * cos_theta * fmaxf(pdf, 1e-6f);                            // CI:177 / 341
-    // CI:124-133: alpha = |acos(dot)|; w_i = 1 (alpha <= alpha_m), linear ramp to 0 at alpha_c, else 0.  acos is
-    // monotone, so the two plateaus are decided on the cosine and acosf only runs on the ramp (rare: the aperture
-    // subtends a few degrees; the ramp is continuous at both ends, so an ulp-level tie is immaterial)
-    const float cdt = dot(P.nT, -sec);
-    float w_i = cdt >= P.cos_m ? 1.0f : 0.0f;
-    if (cdt < P.cos_m && cdt >= P.cos_c) {
-        const float al = fabsf(acosf(cdt));
-        w_i = al <= P.alpha_m ? 1.0f : (al <= P.alpha_c ? (P.alpha_c - al) / (P.alpha_c - P.alpha_m) : 0.0f);
-    }
-    const float w_o = dot(ps.d, h.ns) / P.n_rays;                                // CI:118,184
-    const float press = ps.atten * ps.amp * (w_i * w_o) * sinf(phase);           // CI:187 / 348
     const float kf = rintf(Ttot * P.fs);                                         // CI:191 / 351-352 (half-even)
     int k = (int) kf;
     bool in_range = kf >= 0.0f && kf < (float) P.Tn;
@@ -128,7 +117,25 @@ __device__ __forceinline__ bool segment(const AcqDev &P, const DPrim *prims, Pat
         k = !(kf >= 0.0f) ? 0 : (kf > (float) (P.Tn - 1) ? P.Tn - 1 : k);
         in_range = true;
     }
-    if (visible && in_range) {
+    // The echo's value only matters if it is deposited (CI:197-203 scatter-add under `visible & active`; :353-354):
+    // directivity, sin(phase) and the product are skipped for blocked or out-of-range connections (in the Box scenes
+    // whole warps are blocked together).
+    float press = 0.0f;
+    const bool deposit = visible && in_range;
+    if (deposit || rec) {
+        // CI:124-133: alpha = |acos(dot)|; w_i = 1 (alpha <= alpha_m), linear ramp to 0 at alpha_c, else 0.  acos is
+        // monotone, so the two plateaus are decided on the cosine and acosf only runs on the ramp (rare: the aperture
+        // subtends a few degrees; the ramp is continuous at both ends, so an ulp-level tie is immaterial)
+        const float cdt = dot(P.nT, -sec);
+        float w_i = cdt >= P.cos_m ? 1.0f : 0.0f;
+        if (cdt < P.cos_m && cdt >= P.cos_c) {
+            const float al = fabsf(acosf(cdt));
+            w_i = al <= P.alpha_m ? 1.0f : (al <= P.alpha_c ? (P.alpha_c - al) / (P.alpha_c - P.alpha_m) : 0.0f);
+        }
+        const float w_o = dot(ps.d, h.ns) / P.n_rays;                            // CI:118,184
+        press = ps.atten * ps.amp * (w_i * w_o) * sinf(phase);                   // CI:187 / 348
+    }
+    if (deposit) {
         if (P.buf) atomicAdd(P.buf + ((size_t) ps.a * P.n_e + recv) * (size_t) P.Tn + (size_t) k, press * P.inv_spp);   // CI:197-203 / 354
         cn.deposits++;
     }
