@@ -1,4 +1,5 @@
 #!/bin/bash
+# per-bounce queue counts (PRT_WF_DEBUG), clean launch lists of the default and the cbox bench commands, then the default bench line
 mkdir -p gpurun_out
 PRT_WF_DEBUG=1 python tools/prof_render.py --workload cbox --res 2048 --spp 4 --launches 1 2>&1 | grep "prt wf" > gpurun_out/wf_counts_cbox.txt
 PRT_WF_DEBUG=1 python tools/prof_render.py --workload heightfield --res 3840 --spp 2 --launches 1 2>&1 | grep "prt wf" > gpurun_out/wf_counts_hf.txt
