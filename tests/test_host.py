@@ -134,6 +134,25 @@ def test_reference_cbox_and_meshes_load():
         assert idx.shape == (nt, 3) and (vn is not None) == has_n and idx.max() < len(v)
 
 
+@pytest.mark.skipif(not HAS_REFERENCE, reason="/root/reference is only present in the build container")
+def test_reference_scripts_run_unchanged_up_to_the_gpu_boundary():
+    """The reference's own scripts, byte for byte, through tools/run_reference_script.py: TestScene.py completes;
+    USMain.py gets through its imports, plugin registration, scene dict and mi.load_dict (USMain.py:1-259) and -- in this
+    GPU-less container -- stops at the first compute call (simulate_acquisition_parallel, :99) with a loud error, not
+    with a CPU fallback.  (With a GPU it runs to the end; that call sequence is tests/test_gpu_driver.py.)"""
+    run = [sys.executable, os.path.join(ROOT, "tools", "run_reference_script.py")]
+    r = subprocess.run(run + [os.path.join(REFERENCE, "TestScene.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    n = C.c_int(-1)
+    if capi.load().prt_device_count(C.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a GPU is present: USMain.py would run its 51 acquisitions")
+    r = subprocess.run(run + [os.path.join(REFERENCE, "USMain.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0
+    assert "USMain.py\", line 99, in us_render" in r.stderr and "simulate_acquisition_parallel" in r.stderr
+    assert "PrtError" in r.stderr and ("no CPU fallback" in r.stderr or "CUDA" in r.stderr)
+    assert "ModuleNotFoundError" not in r.stderr and "KeyError" not in r.stderr and "AttributeError" not in r.stderr
+
+
 def test_mesh_readers_roundtrip(tmp_path):
     from prt_b200.meshio import load_obj, load_ply
     p = tmp_path / "q.obj"
