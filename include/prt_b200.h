@@ -143,6 +143,11 @@ int prt_acquire(prt_scene *, const prt_acq_params *, uint64_t seed, uint32_t spp
 int prt_acquire_dev(prt_scene *, const prt_acq_params *, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
                     uint32_t sample_stride, float *channel_buf_dev, float *tx_delays_dev, uint64_t *stats_dev,
                     void *stream);
+/* Same for the steering angles [angle_first, angle_first + angle_count) only (they own disjoint slices of
+ * channel_buf): lets a multi-GPU caller start the all-reduce of one angle's slice while the next angle is traced. */
+int prt_acquire_dev_angles(prt_scene *, const prt_acq_params *, uint64_t seed, uint32_t spp_total,
+                           uint32_t sample_offset, uint32_t sample_stride, int32_t angle_first, int32_t angle_count,
+                           float *channel_buf_dev, float *tx_delays_dev, uint64_t *stats_dev, void *stream);
 
 /* decision-level trace of selected paths (parity tests): rec [n][max_depth] */
 typedef struct {

@@ -338,7 +338,17 @@ extern "C" {
 
 int prt_acquire_dev(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
                     uint32_t sample_stride, float *channel_buf_dev, float *tx_delays_dev, uint64_t *stats_dev, void *stream) {
+    PRT_REQUIRE(s && p, "prt_acquire_dev: null argument");
+    return prt_acquire_dev_angles(s, p, seed, spp_total, sample_offset, sample_stride, 0, p->n_angles, channel_buf_dev, tx_delays_dev,
+                                  stats_dev, stream);
+}
+
+int prt_acquire_dev_angles(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                           uint32_t sample_stride, int32_t angle_first, int32_t angle_count, float *channel_buf_dev,
+                           float *tx_delays_dev, uint64_t *stats_dev, void *stream) {
     PRT_REQUIRE(s && p && channel_buf_dev, "prt_acquire_dev: null argument");
+    PRT_REQUIRE(angle_first >= 0 && angle_count >= 0 && angle_first + angle_count <= p->n_angles, "prt_acquire_dev_angles: angle range out of bounds");
+    if (angle_count == 0) return PRT_OK;
     if (!s->committed) { set_error("prt_acquire_dev: scene not committed"); return PRT_ERR_STATE; }
     std::lock_guard<std::mutex> lk(s->ctx->mtx);
     PRT_CUDA(cudaSetDevice(s->ctx->device));
@@ -355,8 +365,10 @@ int prt_acquire_dev(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32
     // and the warp's rays decohere (measured on B200: ring 42.2 -> 26.5 ms, Sphere_Box intended 13.6 -> 10.3 ms).
     // PRT_ACQ_SPLIT=0 restores the single launch.
     static const bool split = [] { const char *e = getenv("PRT_ACQ_SPLIT"); return !(e && e[0] == '0'); }();
-    if (!split || p->n_angles == 1) return launch_acquire(s->ctx, P, st);
-    for (int a = 0; a < p->n_angles; a++) {
+    P.a_first = angle_first;
+    P.a_count = angle_count;
+    if (!split || angle_count == 1) return launch_acquire(s->ctx, P, st);
+    for (int a = angle_first; a < angle_first + angle_count; a++) {
         AcqDev Q = P;
         Q.a_first = a;
         Q.a_count = 1;

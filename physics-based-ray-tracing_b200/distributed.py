@@ -54,6 +54,23 @@ def _to_pinned(dev_scene, tensor):
     return host
 
 
+def acquire_allreduce_pipelined(dev_scene, params, buf, tx, stats, stream, seed, spp_total, off, stride, dist, world):
+    """The acquisition of one rank + the sum all-reduce of its channel buffer, pipelined by steering angle: angle a's
+    slice of ``buf`` is reduced (NCCL, on the process group's own stream) while angle a + 1 is still being traced, so
+    the collective costs the step nothing but its last slice.  Returns after making ``stream`` wait for the reduces."""
+    if world <= 1:
+        dev_scene.acquire_dev(params, buf.data_ptr(), tx.data_ptr(), stats.data_ptr(), stream.cuda_stream, seed=seed,
+                              spp=spp_total, sample_offset=off, sample_stride=stride)
+        return
+    works = []
+    for a in range(params.n_angles):
+        dev_scene.acquire_dev(params, buf.data_ptr(), tx.data_ptr(), stats.data_ptr(), stream.cuda_stream, seed=seed,
+                              spp=spp_total, sample_offset=off, sample_stride=stride, angle_first=a, angle_count=1)
+        works.append(dist.all_reduce(buf[a], op=dist.ReduceOp.SUM, async_op=True))
+    for w in works:
+        w.wait()
+
+
 def acquire_sharded(dev_scene, params, seed: int, spp_total: int, to_host: bool = True, buf=None, stats=None):
     """Rank-local shard of an acquisition + all-reduce.  Returns (channel_buf, tx_delays, stats) with the
     buffers on the host (numpy, page-locked) if ``to_host`` else as torch CUDA tensors (owned by the scene's cache
@@ -72,10 +89,8 @@ def acquire_sharded(dev_scene, params, seed: int, spp_total: int, to_host: bool 
             stats = _cached(dev_scene, "stats", lambda: torch.empty(8, dtype=torch.int64, device=device))
         stats.zero_()
         stream = torch.cuda.current_stream(device)
-        dev_scene.acquire_dev(params, buf.data_ptr(), tx.data_ptr(), stats.data_ptr(), stream.cuda_stream, seed=seed,
-                              spp=spp_total, sample_offset=off, sample_stride=stride)
+        acquire_allreduce_pipelined(dev_scene, params, buf, tx, stats, stream, seed, spp_total, off, stride, dist, world)
         if world > 1:
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM)       # same stream: runs right behind the path kernel
             dist.all_reduce(stats, op=dist.ReduceOp.SUM)
         if not to_host:
             return buf, tx, stats

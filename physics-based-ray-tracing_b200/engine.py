@@ -186,12 +186,15 @@ class DeviceScene:
         return bufs, tx, [x.as_dict() for x in st]
 
     def acquire_dev(self, params: AcqParams, buf_ptr: int, tx_ptr: int = 0, stats_ptr: int = 0, stream: int = 0,
-                    seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1):
-        """Device-buffer entry point (accumulates into ``buf_ptr`` on ``stream``, asynchronous)."""
+                    seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1, angle_first: int = 0,
+                    angle_count: Optional[int] = None):
+        """Device-buffer entry point (accumulates into ``buf_ptr`` on ``stream``, asynchronous); optionally only the
+        steering angles [angle_first, angle_first + angle_count)."""
         ps = capi.make_acq_params(params)
-        check(self.L.prt_acquire_dev(self.h, C.byref(ps), seed, spp, sample_offset, sample_stride, C.c_void_p(buf_ptr),
-                                     C.c_void_p(tx_ptr or None), C.c_void_p(stats_ptr or None), C.c_void_p(stream or None)),
-              "prt_acquire_dev")
+        n = params.n_angles - angle_first if angle_count is None else angle_count
+        check(self.L.prt_acquire_dev_angles(self.h, C.byref(ps), seed, spp, sample_offset, sample_stride, angle_first, n,
+                                            C.c_void_p(buf_ptr), C.c_void_p(tx_ptr or None), C.c_void_p(stats_ptr or None),
+                                            C.c_void_p(stream or None)), "prt_acquire_dev")
 
     def acquire_trace(self, params: AcqParams, path_idx, seed: int = 0, spp: int = 1) -> np.ndarray:
         ps = capi.make_acq_params(params)
