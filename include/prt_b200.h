@@ -217,6 +217,22 @@ int prt_das_beamform(prt_context *, const prt_das_params *, const float *channel
 int prt_envelope(prt_context *, const float *rf, int32_t nx, int32_t nz, float *envelope);
 
 
+/* ---- the driver's whole us_render() (/root/reference/USMain.py:92-224) in one call, channel data resident on the
+ * device: acquisition -> optional pulse shaping (sigma = wave_cycles / (4 f)) -> delay-and-sum -> envelope -> log
+ * compression (db = 20 log10(env + 1e-12), clipped to [max - dynamic_range_db, max], scaled to [0, 1]).
+ * x [nx], z [nz] host; bmode [nz][nx] (the driver's display_image, :224), envelope [nx][nz] (nullable).  Single GPU:
+ * with sample shards the channel buffers must be all-reduced before beamforming (use prt_acquire_dev + prt_das_beamform). */
+typedef struct {
+    int32_t nx, nz;
+    double  t0, f_number;        /* as prt_das_params */
+    int32_t shape_pulse, _pad;
+    double  wave_cycles;         /* CustomIntegrator.py:20 */
+    double  dynamic_range_db;    /* 60 in the driver (USMain.py:213) */
+} prt_us_render_params;
+int prt_us_render(prt_scene *, const prt_acq_params *, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                  uint32_t sample_stride, const prt_us_render_params *, const float *x, const float *z, float *bmode,
+                  float *envelope /*nullable*/, prt_acq_stats *stats /*nullable*/);
+
 /* ---- "next" row f4: pulse shaping (prototype at /root/reference/RayTracingV0.py:185-204, "UltraRay Eq. 14").
  * channel [n_rows][T] of delta echoes -> out [n_rows][T] = zero-phase convolution of every row with
  * h(t) = sin(2 pi fc t) exp(-t^2 / sigma_s^2), truncated at |t| <= 4 sigma_s (<= 1024 samples either side).

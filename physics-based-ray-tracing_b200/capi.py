@@ -30,7 +30,7 @@ EXPORTS = [
     "prt_scene_create", "prt_scene_destroy", "prt_scene_add_material", "prt_scene_set_material_param",
     "prt_scene_add_primitive", "prt_scene_add_mesh", "prt_scene_commit", "prt_trace_closest", "prt_trace_occluded",
     "prt_ultra_bsdf_sample", "prt_acquire", "prt_acquire_dev", "prt_acquire_dev_angles", "prt_acquire_variants", "prt_acquire_trace", "prt_render_path",
-    "prt_render_path_dev", "prt_render_image", "prt_film_develop_dev", "prt_das_beamform", "prt_envelope", "prt_pulse_shape", "prt_pulse_shape_dev",
+    "prt_render_path_dev", "prt_render_image", "prt_film_develop_dev", "prt_das_beamform", "prt_envelope", "prt_us_render", "prt_pulse_shape", "prt_pulse_shape_dev",
 ]
 
 
@@ -99,6 +99,11 @@ class DasParamsC(C.Structure):
                 ("t0", C.c_double), ("f_number", C.c_double)]
 
 
+class UsRenderParamsC(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("nz", C.c_int32), ("t0", C.c_double), ("f_number", C.c_double), ("shape_pulse", C.c_int32),
+                ("_pad", C.c_int32), ("wave_cycles", C.c_double), ("dynamic_range_db", C.c_double)]
+
+
 SEG_DTYPE = np.dtype([("valid", "i4"), ("prim", "i4"), ("shape", "i4"), ("recv", "i4"), ("visible", "i4"),
                       ("reflect", "i4"), ("k", "i4"), ("survive", "i4"), ("t", "f4"), ("total_time", "f4"),
                       ("press", "f4"), ("amp", "f4"), ("atten", "f4"), ("dir", "f4", (3,))])
@@ -152,6 +157,8 @@ def load():
     L.prt_film_develop_dev.argtypes = [vp, vp, C.c_uint64, vp, vp]
     L.prt_das_beamform.argtypes = [vp, C.POINTER(DasParamsC), fp, fp, dp, fp, fp, fp, fp]
     L.prt_envelope.argtypes = [vp, fp, C.c_int32, C.c_int32, fp]
+    L.prt_us_render.argtypes = [vp, C.POINTER(AcqParamsC), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(UsRenderParamsC),
+                                fp, fp, fp, fp, C.POINTER(AcqStatsC)]
     L.prt_pulse_shape.argtypes = [vp, fp, C.c_uint64, C.c_int32, C.c_double, C.c_double, C.c_double, fp]
     L.prt_pulse_shape_dev.argtypes = [vp, vp, C.c_uint64, C.c_int32, C.c_double, C.c_double, C.c_double, vp, vp]
     _lib = L

@@ -352,7 +352,18 @@ int prt_acquire_dev_angles(prt_scene *s, const prt_acq_params *p, uint64_t seed,
     if (!s->committed) { set_error("prt_acquire_dev: scene not committed"); return PRT_ERR_STATE; }
     std::lock_guard<std::mutex> lk(s->ctx->mtx);
     PRT_CUDA(cudaSetDevice(s->ctx->device));
-    cudaStream_t st = (cudaStream_t) stream;
+    return prt::acquire_enqueue(s, p, seed, spp_total, sample_offset, sample_stride, angle_first, angle_count, channel_buf_dev,
+                                tx_delays_dev, stats_dev, (cudaStream_t) stream);
+}
+
+}  // extern "C"
+
+namespace prt {
+// the launches of prt_acquire_dev_angles; the caller holds the context mutex and has set the device (also used by
+// prt_us_render in prt_das.cu, which chains the post-processing kernels behind it on the same stream)
+int acquire_enqueue(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                    uint32_t sample_stride, int32_t angle_first, int32_t angle_count, float *channel_buf_dev, float *tx_delays_dev,
+                    uint64_t *stats_dev, cudaStream_t st) {
     AcqDev P;
     int rc = fill_params(s, p, seed, spp_total, sample_offset, sample_stride, P, st);
     if (rc) return rc;
@@ -377,6 +388,9 @@ int prt_acquire_dev_angles(prt_scene *s, const prt_acq_params *p, uint64_t seed,
     }
     return PRT_OK;
 }
+}  // namespace prt
+
+extern "C" {
 
 int prt_acquire(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
                 uint32_t sample_stride, float *channel_buf, float *tx_delays, prt_acq_stats *stats) {

@@ -150,9 +150,119 @@ static int launch_pulse(const float *in_d, float *out_d, uint64_t n_rows, int T,
     return PRT_OK;
 }
 
+// log compression of the driver (USMain.py:210-222): db = 20 log10(env + 1e-12); clip to [max - range, max]; scale to
+// [0, 1]; transpose to [nz][nx] (display_image.T).  env >= 0, so max(db) = db(max(env)) and the maximum is found on the
+// envelope itself with an integer atomicMax on the float bits.
+__global__ void __launch_bounds__(256) k_env_max(const float *__restrict__ env, size_t n, unsigned *__restrict__ out) {
+    float m = 0.0f;
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) m = fmaxf(m, env[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+__global__ void __launch_bounds__(256) k_bmode(const float *__restrict__ env, int nx, int nz, const unsigned *__restrict__ mx_bits,
+                                               float dyn_range, float *__restrict__ out) {
+    __shared__ float tile[32][33];
+    const float max_db = 20.0f * log10f(__uint_as_float(*mx_bits) + 1e-12f), min_db = max_db - dyn_range;
+    // 32 x 32 tile transpose: read along z (contiguous in env), write along x (contiguous in out)
+    const int x0 = blockIdx.x * 32, z0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int ix = x0 + r, iz = z0 + tx;
+        if (ix < nx && iz < nz) {
+            const float db = 20.0f * log10f(env[(size_t) ix * nz + iz] + 1e-12f);
+            tile[r][tx] = (fminf(fmaxf(db, min_db), max_db) - min_db) / dyn_range;
+        }
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int iz = z0 + r, ix = x0 + tx;
+        if (ix < nx && iz < nz) out[(size_t) iz * nx + ix] = tile[tx][r];
+    }
+}
+
 }  // namespace prt
 
 using namespace prt;
+
+// The whole us_render() of the reference driver (/root/reference/USMain.py:92-224) behind one call, with the channel data
+// never leaving the device: acquisition (CustomIntegrator.py:235-405) -> optional pulse shaping -> delay-and-sum ->
+// envelope (USMain.py:203-208) -> log compression to the display image (:210-224).  Only the [nz][nx] image (and, if
+// asked for, the envelope) crosses the bus: 2.6 MB instead of 2 x 12.8 MB at the driver's sizes.
+extern "C" int prt_us_render(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                             uint32_t sample_stride, const prt_us_render_params *u, const float *x, const float *z, float *bmode,
+                             float *envelope, prt_acq_stats *stats) {
+    PRT_REQUIRE(s && p && u && x && z && bmode, "prt_us_render: null argument");
+    PRT_REQUIRE(u->nx > 0 && u->nz > 1 && u->nz <= 8192 && u->dynamic_range_db > 0, "prt_us_render: invalid image parameters");
+    if (!s->committed) { set_error("prt_us_render: scene not committed"); return PRT_ERR_STATE; }
+    prt_context *c = s->ctx;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    PRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t n_buf = (size_t) p->n_angles * p->n_elements * (size_t) p->time_samples, n_tx = (size_t) p->n_angles * p->n_elements;
+    const size_t n_px = (size_t) u->nx * u->nz;
+    int rc = ensure_scratch(c, n_buf, n_tx, (size_t) p->n_angles);
+    if (rc) return rc;
+    float *ax_d = nullptr, *rf_d = nullptr, *env_d = nullptr, *img_d = nullptr, *shaped_d = nullptr;
+    if ((rc = scratch_slot(c, 1, sizeof(float) * ((size_t) u->nx + u->nz + 2 * (size_t) p->n_angles + 8), (void **) &ax_d))) return rc;
+    if ((rc = scratch_slot(c, 2, sizeof(float) * n_px, (void **) &rf_d))) return rc;
+    if ((rc = scratch_slot(c, 3, sizeof(float) * n_px, (void **) &env_d))) return rc;
+    if ((rc = scratch_slot(c, 6, sizeof(float) * n_px + 16, (void **) &img_d))) return rc;
+    if (u->shape_pulse && (rc = scratch_slot(c, 5, sizeof(float) * n_buf, (void **) &shaped_d))) return rc;
+    unsigned *mx_d = reinterpret_cast<unsigned *>(img_d + n_px);
+    cudaEvent_t e0, e1, e2;
+    PRT_CUDA(cudaEventCreate(&e0)); PRT_CUDA(cudaEventCreate(&e1)); PRT_CUDA(cudaEventCreate(&e2));
+    PRT_CUDA(cudaEventRecord(e0, st));
+    PRT_CUDA(cudaMemsetAsync(c->acc_dev, 0, sizeof(float) * n_buf, st));
+    PRT_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(uint64_t) * 8, st));
+    PRT_CUDA(cudaMemsetAsync(mx_d, 0, sizeof(unsigned), st));
+    rc = acquire_enqueue(s, p, seed, spp_total, sample_offset, sample_stride, 0, p->n_angles, c->acc_dev, c->aux_dev, c->stats_dev, st);
+    if (rc) return rc;
+    const float *ch_d = c->acc_dev;
+    if (u->shape_pulse) {
+        rc = launch_pulse(c->acc_dev, shaped_d, (uint64_t) n_tx, p->time_samples, p->fs, p->frequency, u->wave_cycles / (4.0 * p->frequency), st);
+        if (rc) return rc;
+        ch_d = shaped_d;
+    }
+    float *x_d = ax_d, *z_d = ax_d + u->nx;
+    float2 *sc_d = reinterpret_cast<float2 *>(ax_d + ((u->nx + u->nz + 1) & ~1));
+    std::vector<float2> sc(p->n_angles);
+    for (int a = 0; a < p->n_angles; a++) {
+        double th = p->angles_deg[a] * M_PI / 180.0;
+        sc[a] = make_float2((float) std::sin(th), (float) std::cos(th));
+    }
+    PRT_CUDA(cudaMemcpyAsync(x_d, x, sizeof(float) * u->nx, cudaMemcpyHostToDevice, st));
+    PRT_CUDA(cudaMemcpyAsync(z_d, z, sizeof(float) * u->nz, cudaMemcpyHostToDevice, st));
+    PRT_CUDA(cudaMemcpyAsync(sc_d, sc.data(), sizeof(float2) * p->n_angles, cudaMemcpyHostToDevice, st));
+    DasDev P;
+    P.n_a = p->n_angles; P.n_e = p->n_elements; P.T = p->time_samples; P.nx = u->nx; P.nz = u->nz;
+    P.fs = (float) p->fs; P.inv_c = (float) (1.0 / p->sound_speed); P.pitch = (float) p->pitch; P.t0 = (float) u->t0;
+    P.f_number = (float) u->f_number;
+    P.channel = ch_d; P.x = x_d; P.z = z_d; P.sincos = sc_d; P.rf = rf_d;
+    k_das<<<dim3((u->nz + 255) / 256, u->nx), 256, 0, st>>>(P);
+    const size_t smem = envelope_smem(u->nz);
+    if (smem > 48 * 1024) PRT_CUDA(cudaFuncSetAttribute(k_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    k_envelope<<<u->nx, 256, smem, st>>>(rf_d, env_d, u->nx, u->nz);
+    k_env_max<<<c->sm_count * 4, 256, 0, st>>>(env_d, n_px, mx_d);
+    k_bmode<<<dim3((u->nx + 31) / 32, (u->nz + 31) / 32), 256, 0, st>>>(env_d, u->nx, u->nz, mx_d, (float) u->dynamic_range_db, img_d);
+    PRT_CUDA(cudaGetLastError());
+    PRT_CUDA(cudaEventRecord(e1, st));
+    PRT_CUDA(cudaMemcpyAsync(bmode, img_d, sizeof(float) * n_px, cudaMemcpyDeviceToHost, st));
+    if (envelope) PRT_CUDA(cudaMemcpyAsync(envelope, env_d, sizeof(float) * n_px, cudaMemcpyDeviceToHost, st));
+    uint64_t hs[8];
+    PRT_CUDA(cudaMemcpyAsync(hs, c->stats_dev, sizeof hs, cudaMemcpyDeviceToHost, st));
+    PRT_CUDA(cudaEventRecord(e2, st));
+    PRT_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        stats->paths = hs[0]; stats->segments = hs[1]; stats->rays = hs[2]; stats->deposits = hs[3]; stats->misses = hs[4];
+        PRT_CUDA(cudaEventElapsedTime(&stats->kernel_ms, e0, e1));
+        PRT_CUDA(cudaEventElapsedTime(&stats->total_ms, e0, e2));
+        stats->launches = (uint32_t) p->n_angles + 4u + (u->shape_pulse ? 1u : 0u);
+        stats->_pad = 0;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return PRT_OK;
+}
 
 extern "C" int prt_pulse_shape_dev(prt_context *c, const float *channel_dev, uint64_t n_rows, int32_t time_samples, double fs,
                                    double fc, double sigma_s, float *out_dev, void *stream) {

@@ -129,5 +129,8 @@ int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, cons
                float4 **out_nodes8, uint32_t *out_n_nodes8, float4 **out_tri_v8, uint32_t **out_tri8_sorted, int *out_levels,
                cudaStream_t st);
 int ensure_scratch(prt_context *ctx, size_t acc_floats, size_t aux_floats, size_t n_angles);
-int scratch_slot(prt_context *ctx, int slot, size_t bytes, void **out);   // grow-only; contents undefined after growth
+int scratch_slot(prt_context *ctx, int slot, size_t bytes, void **out);
+int acquire_enqueue(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                    uint32_t sample_stride, int32_t angle_first, int32_t angle_count, float *channel_buf_dev, float *tx_delays_dev,
+                    uint64_t *stats_dev, cudaStream_t st);   // grow-only; contents undefined after growth
 }  // namespace prt

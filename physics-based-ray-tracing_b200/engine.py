@@ -185,6 +185,22 @@ class DeviceScene:
                                           dptr(vals), vals.size, fptr(bufs), fptr(tx), st), "prt_acquire_variants")
         return bufs, tx, [x.as_dict() for x in st]
 
+    def us_render(self, params: AcqParams, x, z, seed: int = 0, spp: int = 1, t0: float = 0.0, f_number: float = 1.0,
+                  dynamic_range: float = 60.0, shape_pulse: bool = False, wave_cycles: float = 5.0, want_envelope: bool = True):
+        """The driver's us_render() (USMain.py:92-224) in one library call, channel data resident on the device.
+        Returns (display_image [nz, nx] in [0, 1], envelope [nx, nz] or None, stats)."""
+        ps = capi.make_acq_params(params)
+        xs = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        zs = np.ascontiguousarray(z, dtype=np.float32).reshape(-1)
+        u = capi.UsRenderParamsC(xs.size, zs.size, float(t0), float(f_number), int(bool(shape_pulse)), 0, float(wave_cycles),
+                                 float(dynamic_range))
+        img = self.ctx.pinned_array((zs.size, xs.size), np.float32)
+        env = self.ctx.pinned_array((xs.size, zs.size), np.float32) if want_envelope else None
+        st = capi.AcqStatsC()
+        check(self.L.prt_us_render(self.h, C.byref(ps), seed, spp, 0, 1, C.byref(u), fptr(xs), fptr(zs), fptr(img), fptr(env),
+                                   C.byref(st)), "prt_us_render")
+        return img, env, st.as_dict()
+
     def acquire_dev(self, params: AcqParams, buf_ptr: int, tx_ptr: int = 0, stats_ptr: int = 0, stream: int = 0,
                     seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1, angle_first: int = 0,
                     angle_count: Optional[int] = None):

@@ -146,6 +146,20 @@ class UltraIntegrator(mi.SamplingIntegrator):
             bufs = pulse_shape(bufs, self.fs, self.frequency, wave_cycles=self.wave_cycles, context=scene.device().ctx)
         return bufs
 
+    def render_bmode(self, scene, x_scan, z_scan, dynamic_range=60.0, f_number=1.0, t0=0.0):
+        """Extension: everything us_render() of the driver does after ``scene.integrator()`` (USMain.py:99-224) --
+        acquisition, delay-and-sum, envelope, log compression -- in ONE library call with the channel data resident on the
+        device (prt_us_render).  Returns the driver's ``display_image`` ([len(z_scan), len(x_scan)], values in [0, 1]);
+        the envelope is left on ``self.last_envelope``.  Single GPU."""
+        p = self.acq_params(scene)
+        p.quirk_flags = self.quirk_flags
+        img, env, st = scene.device().us_render(p, x_scan, z_scan, seed=self.seed, spp=max(int(self.samples_per_element), 1),
+                                                t0=t0, f_number=f_number, dynamic_range=dynamic_range,
+                                                shape_pulse=self.shape_pulse, wave_cycles=self.wave_cycles)
+        self.last_stats, self.last_envelope = st, env
+        self.ray_count += int(st["segments"])
+        return img
+
     def traverse(self, callback):
         callback.put_parameter('pitch', self.pitch, mi.ParamFlags.Differentiable)
 

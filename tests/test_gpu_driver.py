@@ -92,6 +92,39 @@ def test_pulse_shape_matches_oracle():
     assert np.abs(lhs - rhs).max() <= 1e-4 * np.abs(lhs).max()
 
 
+@pytest.mark.parametrize("shape_pulse", [False, True])
+def test_us_render_equals_the_staged_pipeline(shape_pulse):
+    """prt_us_render (acquisition -> pulse shaping -> DAS -> envelope -> log compression on the device) against the same
+    stages run one by one the way the driver does (USMain.py:99-224: simulate_acquisition_parallel, DelayAndSum.beamform,
+    compute_envelope, numpy log compression), same seed."""
+    from prt_b200 import mi_compat as mi
+    from prt_b200.engine import das_beamform
+    d = scenes.usmain_scene_dict()
+    d["integrator"]["angles"] = np.linspace(-15, 15, 5)
+    d["integrator"]["samples_per_element"] = 32
+    d["integrator"]["shape_pulse"] = shape_pulse
+    scene = mi.load_dict(d)
+    integ = scene.integrator()
+    lam = integ.sound_speed / integ.frequency
+    x = np.arange(-0.02, 0.02 + lam / 2, lam / 2)
+    z = np.arange(0.001, 0.05 + lam / 4, lam / 4)              # ragged: neither a multiple of 32 nor of 256
+    img = integ.render_bmode(scene, x, z, dynamic_range=60.0, f_number=1.0)
+    st = integ.last_stats
+    assert img.shape == (len(z), len(x)) and img.dtype == np.float32
+    assert 0.0 <= img.min() and img.max() == pytest.approx(1.0, abs=1e-6)
+    integ.simulate_acquisition_parallel(scene)                   # applies the pulse shaping itself when shape_pulse is set
+    assert integ.last_stats["paths"] == st["paths"] and integ.last_stats["deposits"] == st["deposits"]
+    rf, env = das_beamform(integ.channel_buf, integ.angles.numpy(), x, z, integ.fs, integ.sound_speed, integ.pitch, f_number=1.0)
+    assert np.abs(integ.last_envelope - env).max() <= 1e-4 * env.max()
+    db = 20 * np.log10(env.astype(np.float32) + np.float32(1e-12))
+    mx = db.max()
+    ref = ((np.clip(db, mx - 60, mx) - (mx - 60)) / 60).T
+    # the display image is a log of the envelope: compare where the envelope is well above the 60 dB floor, and the
+    # clipped floor itself
+    assert np.abs(img - ref).max() <= 2e-3
+    assert ((img == 0) == (ref == 0)).mean() > 0.999
+
+
 def test_sharded_entry_points_single_rank():
     """distributed.acquire_sharded / render_sharded without a process group (world size 1) == the plain calls; the
     multi-rank arithmetic (shard_samples + one sum all-reduce) is covered by the gloo test and by sharded == unsharded."""

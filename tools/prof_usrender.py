@@ -29,3 +29,10 @@ for it in range(4):
     ps = pulse_shape(ch, integ.fs, integ.frequency, wave_cycles=5)
     t4 = time.perf_counter()
     print(f"iter {it}: acquire {1e3*(t1-t0):.2f} ms, DAS+envelope {1e3*(t2-t1):.2f} ms ({x.size}x{z.size} px), log-compress (numpy) {1e3*(t3-t2):.2f} ms, pulse_shape {1e3*(t4-t3):.2f} ms; lib kernel {integ.last_stats['kernel_ms']:.3f} ms")
+
+for it in range(4):
+    t0 = time.perf_counter()
+    img = integ.render_bmode(scene, x, z, dynamic_range=60.0)
+    t1 = time.perf_counter()
+    st = integ.last_stats
+    print(f"render_bmode iter {it}: wall {1e3*(t1-t0):.2f} ms (device {st['kernel_ms']:.3f} ms, with D2H {st['total_ms']:.3f} ms), image {img.shape}")
