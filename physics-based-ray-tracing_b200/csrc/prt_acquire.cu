@@ -407,8 +407,9 @@ int prt_acquire(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t s
     const size_t n_tx = (size_t) p->n_angles * p->n_elements;
     rc = ensure_scratch(c, n_buf, n_tx, (size_t) p->n_angles);
     if (rc) return rc;
-    cudaEvent_t e0, e1, e2, e3;
-    PRT_CUDA(cudaEventCreate(&e0)); PRT_CUDA(cudaEventCreate(&e1)); PRT_CUDA(cudaEventCreate(&e2)); PRT_CUDA(cudaEventCreate(&e3));
+    ScopedEvents<4> ev;
+    PRT_REQUIRE(ev.ok, "cudaEventCreate failed");
+    cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2], e3 = ev.e[3];
     PRT_CUDA(cudaEventRecord(e0, st));
     PRT_CUDA(cudaMemsetAsync(c->acc_dev, 0, sizeof(float) * n_buf, st));
     PRT_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(uint64_t) * 8, st));
@@ -461,7 +462,6 @@ int prt_acquire(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t s
         stats->launches = launches;
         stats->_pad = 0;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     return PRT_OK;
 }
 
@@ -493,8 +493,9 @@ int prt_acquire_variants(prt_scene *s, const prt_acq_params *p, uint64_t seed, u
     const size_t n_tx = (size_t) p->n_angles * p->n_elements;
     rc = ensure_scratch(c, n_buf * n_values, n_tx, (size_t) p->n_angles);
     if (rc) return rc;
-    cudaEvent_t e0, e1, e2;
-    PRT_CUDA(cudaEventCreate(&e0)); PRT_CUDA(cudaEventCreate(&e1)); PRT_CUDA(cudaEventCreate(&e2));
+    ScopedEvents<3> ev;
+    PRT_REQUIRE(ev.ok, "cudaEventCreate failed");
+    cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2];
     PRT_CUDA(cudaEventRecord(e0, st));
     PRT_CUDA(cudaMemsetAsync(c->acc_dev, 0, sizeof(float) * n_buf * n_values, st));
     PRT_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(uint64_t) * 8 * PRT_MAX_VARIANTS, st));
@@ -540,7 +541,6 @@ int prt_acquire_variants(prt_scene *s, const prt_acq_params *p, uint64_t seed, u
             stats[v]._pad = 0;
         }
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return PRT_OK;
 }
 

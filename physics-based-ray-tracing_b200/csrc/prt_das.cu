@@ -210,8 +210,9 @@ extern "C" int prt_us_render(prt_scene *s, const prt_acq_params *p, uint64_t see
     if ((rc = scratch_slot(c, 6, sizeof(float) * n_px + 16, (void **) &img_d))) return rc;
     if (u->shape_pulse && (rc = scratch_slot(c, 5, sizeof(float) * n_buf, (void **) &shaped_d))) return rc;
     unsigned *mx_d = reinterpret_cast<unsigned *>(img_d + n_px);
-    cudaEvent_t e0, e1, e2;
-    PRT_CUDA(cudaEventCreate(&e0)); PRT_CUDA(cudaEventCreate(&e1)); PRT_CUDA(cudaEventCreate(&e2));
+    ScopedEvents<3> ev;
+    PRT_REQUIRE(ev.ok, "cudaEventCreate failed");
+    cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2];
     PRT_CUDA(cudaEventRecord(e0, st));
     PRT_CUDA(cudaMemsetAsync(c->acc_dev, 0, sizeof(float) * n_buf, st));
     PRT_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(uint64_t) * 8, st));
@@ -260,7 +261,6 @@ extern "C" int prt_us_render(prt_scene *s, const prt_acq_params *p, uint64_t see
         stats->launches = (uint32_t) p->n_angles + 4u + (u->shape_pulse ? 1u : 0u);
         stats->_pad = 0;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return PRT_OK;
 }
 

@@ -28,6 +28,23 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         }                                    \
     } while (0)
 
+// N timing events that are destroyed on every exit path (the entry points return early on the first CUDA error)
+template <int N>
+struct ScopedEvents {
+    cudaEvent_t e[N];
+    bool ok = true;
+    ScopedEvents() {
+        for (int i = 0; i < N; i++) e[i] = nullptr;
+        for (int i = 0; i < N && ok; i++) ok = cudaEventCreate(&e[i]) == cudaSuccess;
+    }
+    ~ScopedEvents() {
+        for (int i = 0; i < N; i++)
+            if (e[i]) cudaEventDestroy(e[i]);
+    }
+    ScopedEvents(const ScopedEvents &) = delete;
+    ScopedEvents &operator=(const ScopedEvents &) = delete;
+};
+
 struct HostMesh {
     std::vector<float> v;   // [nt][3][3] world space
     std::vector<float> n;   // [nt][3][3] world-space corner normals (if has_n)

@@ -218,8 +218,9 @@ static int render_host(prt_scene *s, const prt_render_params *p, uint64_t seed, 
     const size_t n_out = develop ? n / 4 * 3 : n;
     rc = ensure_scratch(c, n, develop ? n_out : 0, 0);
     if (rc) return rc;
-    cudaEvent_t e0, e1, e2, e3;
-    PRT_CUDA(cudaEventCreate(&e0)); PRT_CUDA(cudaEventCreate(&e1)); PRT_CUDA(cudaEventCreate(&e2)); PRT_CUDA(cudaEventCreate(&e3));
+    ScopedEvents<4> ev;
+    PRT_REQUIRE(ev.ok, "cudaEventCreate failed");
+    cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2], e3 = ev.e[3];
     PRT_CUDA(cudaEventRecord(e0, st));
     PRT_CUDA(cudaMemsetAsync(c->acc_dev, 0, sizeof(float) * n, st));
     PRT_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(uint64_t) * 8, st));
@@ -254,7 +255,6 @@ static int render_host(prt_scene *s, const prt_render_params *p, uint64_t seed, 
         stats->launches = (uint32_t) c->last_launches;
         stats->_pad = 0;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     return PRT_OK;
 }
 
