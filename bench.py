@@ -548,6 +548,22 @@ def main():
             line["cpu_baseline"] = {"value": rays_c / t_c / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
                                     "sample": f"{reps} x {C1_SPP * n_ae} paths (BASELINE config 1 path count) of the same scene, "
                                               f"oracle f32, {threads} threads, {t_c:.1f} s"}
+            # SURVEY 8(d) also asks for (ii) the restatement on ONE thread and (iii) a pure-Python transliteration of
+            # _trace_single_ray on the literal 320-path acquisition, as a proxy for the reference's interpreter-bound loop
+            st1, dt1 = cpu_oracle_rate(desc, p, C1_SPP, 0, 1)
+            line["cpu_baseline"]["single_thread"] = {"value": st1["rays"] / dt1 / 1e6, "unit": "Mrays/s", "cores": 1,
+                                                     "sample": f"{C1_SPP * n_ae} paths, oracle f32, {dt1:.1f} s"}
+            try:
+                import pyref
+                shapes_py = pyref.shapes_from_desc(desc)
+                t0 = time.perf_counter()
+                _, _, stp = pyref.acquire(shapes_py, p, seed=0, spp=1)
+                dtp = time.perf_counter() - t0
+                line["cpu_baseline"]["pure_python"] = {"value": stp["rays"] / dtp / 1e6, "unit": "Mrays/s", "cores": 1,
+                                                       "sample": f"{n_ae} paths (the reference's literal acquisition: 1 path per "
+                                                                 f"(angle, element)), oracle/pyref.py, {dtp:.2f} s"}
+            except ValueError:
+                pass                         # pyref handles sphere / rectangle scenes only
     else:
         line = None
     if not args.no_also:
