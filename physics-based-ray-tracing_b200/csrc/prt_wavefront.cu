@@ -39,14 +39,16 @@ namespace prt {
 static constexpr unsigned FULL = 0xffffffffu;
 static constexpr int WF_QUEUES = 3;        // shading queues: 0 diffuse, 1 dielectric, 2 everything else (conductor, null)
 static constexpr int WF_CSTRIDE = 16;      // ints per bounce in the counter array
-static constexpr int WF_CHUNK = 64;        // rays a warp reserves per atomic on the queue head
+#ifndef WF_CHUNK
+#define WF_CHUNK 64                        // rays a warp reserves per atomic on the queue head
+#endif
 static constexpr int WF_TRACE_THREADS = 128;
 static constexpr int WF_SHADE_THREADS = 256;
 #ifndef WF_SHADE_MINB
 #define WF_SHADE_MINB 2                   // min resident CTAs per SM the shading kernels are compiled for
 #endif
 #ifndef WF_COOP_MAX
-#define WF_COOP_MAX 12                     // warp-cooperative triangle tests while at most this many lanes hold triangles
+#define WF_COOP_MAX 16                     // warp-cooperative triangle tests while at most this many lanes hold triangles
 #endif
 #ifndef WF_REFILL_MIN
 #define WF_REFILL_MIN 1                    // idle lanes before a warp goes back to the queue
