@@ -75,6 +75,23 @@ static constexpr uint32_t WF_HOLE = 0xffffffffu;   // unused tail of a warp's re
 // 64-bit word, so a shading warp reserves both of its output ranges with a single atomic.
 enum { C_EXT = 0, C_MAT = 1, C_HEAD_EXT = 8, C_HEAD_SH = 12, C_SH = WF_CSTRIDE - 1 };
 
+// The wavefront's own streams (ray records, path state, hit records, queues) are written once and read once, gigabytes
+// apart; evict-first hints (ld/st.global.cs) were meant to stop them displacing BVH nodes and triangles from L2.  Measured
+// on B200: no gain (height field 1 910 vs 1 932 Mrays/s, cbox 6 540 vs 6 577) -- L2's own replacement already keeps the
+// hot upper levels.  Left as a build knob, off.
+#ifndef WF_STREAM_HINTS
+#define WF_STREAM_HINTS 0
+#endif
+#if WF_STREAM_HINTS
+__device__ __forceinline__ float4 ld_stream(const float4 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4 *p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(uint32_t *p, uint32_t v) { __stcs(p, v); }
+#else
+__device__ __forceinline__ float4 ld_stream(const float4 *p) { return *p; }
+__device__ __forceinline__ void st_stream(float4 *p, float4 v) { *p = v; }
+__device__ __forceinline__ void st_stream(uint32_t *p, uint32_t v) { *p = v; }
+#endif
+
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -128,16 +145,16 @@ __device__ __forceinline__ int wf_reserve(int *counter, bool pred) {
 __device__ __forceinline__ void wf_write_ray(const WfRays &R, int pos, float3 o, float3 d, float tmax, uint32_t slot, float extra) {
     const RayPre rp = ray_precompute(d);
     const Bvh8Ray r8 = bvh8_ray(o, d);
-    R.r0[pos] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
-    R.r1[pos] = make_float4(d.x, d.y, d.z, tmax);
-    R.r2[pos] = make_float4(r8.inv.x, r8.inv.y, r8.inv.z, extra);
-    R.r3[pos] = make_float4(rp.Sx, rp.Sy, rp.Sz, __int_as_float(rp.kx | (rp.ky << 2) | (rp.kz << 4)));
+    st_stream(R.r0 + pos, make_float4(o.x, o.y, o.z, __uint_as_float(slot)));
+    st_stream(R.r1 + pos, make_float4(d.x, d.y, d.z, tmax));
+    st_stream(R.r2 + pos, make_float4(r8.inv.x, r8.inv.y, r8.inv.z, extra));
+    st_stream(R.r3 + pos, make_float4(rp.Sx, rp.Sy, rp.Sz, __int_as_float(rp.kx | (rp.ky << 2) | (rp.kz << 4))));
 }
 
 __device__ __forceinline__ void wf_load_state(const WfBuf &B, uint32_t slot, PtState &st) {
     const float4 *rec = B.ST + 8 * (size_t) slot;
-    float4 a = rec[0], b = rec[1], c = rec[2], d = rec[3], e = rec[4];
-    const float4 rr = rec[5];
+    float4 a = ld_stream(rec), b = ld_stream(rec + 1), c = ld_stream(rec + 2), d = ld_stream(rec + 3), e = ld_stream(rec + 4);
+    const float4 rr = ld_stream(rec + 5);
     uint4 r = make_uint4(__float_as_uint(rr.x), __float_as_uint(rr.y), __float_as_uint(rr.z), __float_as_uint(rr.w));
     st.o = xyz(a); st.px = a.w;
     st.d = xyz(b); st.py = b.w;
@@ -153,13 +170,13 @@ __device__ __forceinline__ void wf_load_state(const WfBuf &B, uint32_t slot, PtS
 
 __device__ __forceinline__ void wf_store_state(const WfBuf &B, uint32_t slot, const PtState &st) {
     float4 *rec = B.ST + 8 * (size_t) slot;
-    rec[0] = make_float4(st.o.x, st.o.y, st.o.z, st.px);
-    rec[1] = make_float4(st.d.x, st.d.y, st.d.z, st.py);
-    rec[2] = make_float4(st.thr.x, st.thr.y, st.thr.z, st.eta);
-    rec[3] = make_float4(st.res.x, st.res.y, st.res.z, st.prev_pdf);
-    rec[4] = make_float4(st.prev_p.x, st.prev_p.y, st.prev_p.z, __int_as_float(st.depth | ((int) st.prev_delta << 16)));
-    rec[5] = make_float4(__uint_as_float((uint32_t) st.rng.state), __uint_as_float((uint32_t) (st.rng.state >> 32)),
-                         __uint_as_float((uint32_t) st.rng.inc), __uint_as_float((uint32_t) (st.rng.inc >> 32)));
+    st_stream(rec, make_float4(st.o.x, st.o.y, st.o.z, st.px));
+    st_stream(rec + 1, make_float4(st.d.x, st.d.y, st.d.z, st.py));
+    st_stream(rec + 2, make_float4(st.thr.x, st.thr.y, st.thr.z, st.eta));
+    st_stream(rec + 3, make_float4(st.res.x, st.res.y, st.res.z, st.prev_pdf));
+    st_stream(rec + 4, make_float4(st.prev_p.x, st.prev_p.y, st.prev_p.z, __int_as_float(st.depth | ((int) st.prev_delta << 16))));
+    st_stream(rec + 5, make_float4(__uint_as_float((uint32_t) st.rng.state), __uint_as_float((uint32_t) (st.rng.state >> 32)),
+                         __uint_as_float((uint32_t) st.rng.inc), __uint_as_float((uint32_t) (st.rng.inc >> 32))));
 }
 
 // slot -> pixel: a layer (one sample of every pixel) is laid out tile by tile, 256 slots per 16 x 16 tile, and the 32
@@ -269,7 +286,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                         const int kind = __ldg(&sc.mats[prims[best_prim].material].kind);
                         qi = kind == PRT_MAT_DIFFUSE ? 0 : (kind == PRT_MAT_DIELECTRIC ? 1 : 2);
                     }
-                    B.ST[8 * (size_t) slot + 6] = make_float4(t, b1, b2, __int_as_float(id));
+                    st_stream(B.ST + 8 * (size_t) slot + 6, make_float4(t, b1, b2, __int_as_float(id)));
                     if (id >= 0) n_valid++;
                 }
 #if WF_SLOT_SHADE
@@ -289,7 +306,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                         if (lane == 0) fresh = atomicAdd(C + C_MAT + k, WF_QCHUNK);
                         fresh = __shfl_sync(FULL, fresh, 0);
                     }
-                    if (qi == k) B.q_mat[k][rank < room ? next + rank : fresh + (rank - room)] = slot;
+                    if (qi == k) st_stream(B.q_mat[k] + (rank < room ? next + rank : fresh + (rank - room)), slot);
                     __syncwarp();
                     if (lane == 0) {
                         if (cnt > room) { qc[2 * k] = fresh + (cnt - room); qc[2 * k + 1] = fresh + WF_QCHUNK; }
@@ -305,14 +322,14 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                 }
 #endif
             } else if (fin && best < 0 && best_prim < 0) {
-                const float4 c = B.SHC[qpos];
-                const float w = R.r2[qpos].w;
+                const float4 c = ld_stream(B.SHC + qpos);
+                const float w = ld_stream(R.r2 + qpos).w;
                 float4 *acc = B.ST + 8 * (size_t) slot + 3;
-                float4 r = *acc;
+                float4 r = ld_stream(acc);
                 r.x = fmaf(c.x, w, r.x);
                 r.y = fmaf(c.y, w, r.y);
                 r.z = fmaf(c.z, w, r.z);
-                *acc = r;
+                st_stream(acc, r);
             }
             if (fin) has = false;
         }
@@ -347,7 +364,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                 const bool take = !has && rank < avail;
                 if (take) {
                     qpos = (uint32_t) (pool_next + rank);
-                    const float4 a = R.r0[qpos], c2 = R.r2[qpos], c3 = R.r3[qpos];
+                    const float4 a = ld_stream(R.r0 + qpos), c2 = ld_stream(R.r2 + qpos), c3 = ld_stream(R.r3 + qpos);
                     r8.o = xyz(a);
                     slot = __float_as_uint(a.w);
                     r8.inv = xyz(c2);
@@ -363,7 +380,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                     tbest = PRT_INF;
                     bool blocked = false;
                     if (sc.n_prims > 0 || ANY) {
-                        const float4 bb = R.r1[qpos];
+                        const float4 bb = ld_stream(R.r1 + qpos);
                         tbest = bb.w;
                         prim_t = tbest;
                         const float3 d = xyz(bb);
@@ -577,7 +594,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(co
         }
         if (mine) {
             wf_load_state(B, slot, st);
-            const float4 hv = B.ST[8 * (size_t) slot + 6];
+            const float4 hv = ld_stream(B.ST + 8 * (size_t) slot + 6);
             const int id = __float_as_int(hv.w);
             Hit h;
             if (id >= P.sc.n_prims) fill_tri_hit(P.sc, id - P.sc.n_prims, hv.x, hv.y, hv.z, h);
@@ -602,7 +619,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(co
         const int e = (int) (base2 >> 32) + __popc(m_ex & lanemask_lt());
         if (sr.want) {
             wf_write_ray(B.sh, j, sr.o, sr.d, sr.tmax, slot, sr.w);
-            B.SHC[j] = make_float4(sr.c.x, sr.c.y, sr.c.z, 0.0f);
+            st_stream(B.SHC + j, make_float4(sr.c.x, sr.c.y, sr.c.z, 0.0f));
         }
         if (live) wf_write_ray(Rn, e, st.o, st.d, PRT_INF, slot, 0.0f);
     }
