@@ -79,6 +79,9 @@ enum { C_EXT = 0, C_MAT = 1, C_HEAD_EXT = 8, C_HEAD_SH = 12, C_SH = WF_CSTRIDE -
 // apart; evict-first hints (ld/st.global.cs) were meant to stop them displacing BVH nodes and triangles from L2.  Measured
 // on B200: no gain (height field 1 910 vs 1 932 Mrays/s, cbox 6 540 vs 6 577) -- L2's own replacement already keeps the
 // hot upper levels.  Left as a build knob, off.
+#ifndef WF_SHADE_PREFETCH
+#define WF_SHADE_PREFETCH 0
+#endif
 #ifndef WF_STREAM_HINTS
 #define WF_STREAM_HINTS 0
 #endif
@@ -577,6 +580,21 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(co
     const WfRays Rn = B.ext[(bounce + 1) & 1];
     for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
         const int i = i0 + threadIdx.x;
+#if WF_SHADE_PREFETCH
+        {   // the next iteration's inputs are at known addresses: pull them towards L2 while this one computes.  Measured on
+            // B200: nothing gained (cbox shade 22.1 vs 21.6 ms, height field 13.7 vs 13.7) -- off by default
+            const long long i_next = (long long) i + (long long) gridDim.x * blockDim.x;
+            if (i_next < n) {
+                if (by_slot) {
+                    const char *rec = reinterpret_cast<const char *>(B.ST + 8 * (size_t) i_next);
+                    prefetch_l2(rec); prefetch_l2(rec + 32); prefetch_l2(rec + 64); prefetch_l2(rec + 96);
+                    if ((threadIdx.x & 31) == 0) prefetch_l2(B.tag + i_next);
+                } else if ((threadIdx.x & 7) == 0) {
+                    prefetch_l2(q + i_next);
+                }
+            }
+        }
+#endif
         bool live = false;
         uint32_t slot = 0;
         ShadowReq sr;
