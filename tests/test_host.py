@@ -254,6 +254,23 @@ assert torch.equal(buf, torch.ones(9)), buf
 st = torch.tensor([n], dtype=torch.int64)
 allreduce_sum_(st)
 assert int(st[0]) == 9
+# the per-angle pipelined reduce (acquire_allreduce_pipelined): a stand-in scene fills angle a's slice when its launch
+# is requested; every slice must come back summed over ranks, whatever order the asynchronous reduces complete in
+from prt_b200.distributed import acquire_allreduce_pipelined
+class _Params: n_angles = 5
+class _Stream: cuda_stream = 0
+class _FakeScene:
+    def __init__(self, buf): self.buf, self.calls = buf, []
+    def acquire_dev(self, params, buf_ptr, tx_ptr, stats_ptr, stream, seed=0, spp=1, sample_offset=0, sample_stride=1,
+                    angle_first=0, angle_count=None):
+        self.calls.append((angle_first, angle_count, sample_offset, sample_stride))
+        self.buf[angle_first] += float(10 * (rank + 1) + angle_first)
+pbuf = torch.zeros(5, 7)
+fake = _FakeScene(pbuf)
+acquire_allreduce_pipelined(fake, _Params(), pbuf, torch.zeros(1), torch.zeros(1), _Stream(), 0, 4, rank, 2, dist, 2)
+assert fake.calls == [(a, 1, rank, 2) for a in range(5)], fake.calls
+for a in range(5):
+    assert torch.equal(pbuf[a], torch.full((7,), float(10 + 20 + 2 * a))), (a, pbuf[a])
 dist.destroy_process_group()
 print("ok", rank)
 '''
