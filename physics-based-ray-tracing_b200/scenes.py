@@ -241,8 +241,21 @@ def furnace_scene_dict(res: int = 16, spp: int = 64, max_depth: int = 6, rho: fl
     return d
 
 
-def furnace_scene(res: int = 16, spp: int = 64, max_depth: int = 6, rho: float = 0.5, rr_depth: int = 1000) -> SceneDesc:
-    desc = load_dict_desc(furnace_scene_dict(res, spp, max_depth, rho, rr_depth))
+def furnace_scene(res: int = 16, spp: int = 64, max_depth: int = 6, rho: float = 0.5, rr_depth: int = 1000,
+                  spheres: bool = False) -> SceneDesc:
+    """``spheres``: put a smooth glass sphere and a perfect mirror sphere (the two specular BSDFs of scenes/cbox.xml:42-54)
+    into the furnace, in view of the camera.  Neither absorbs, so with a deep enough ``max_depth`` the radiance stays
+    1 / (1 - rho) everywhere -- also through and on the spheres (Fresnel reflection + transmission sum to one and the
+    eta^2 radiance scaling cancels on the way out)."""
+    d = furnace_scene_dict(res, spp, max_depth, rho, rr_depth)
+    if spheres:
+        d["glass"] = {"type": "dielectric"}
+        d["mirror"] = {"type": "conductor"}
+        d["glasssphere"] = {"type": "sphere", "to_world": _xf([T().scale(0.35), T().translate([0.45, -0.3, -0.6])], "mitsuba"),
+                            "bsdf": {"type": "ref", "id": "glass"}}
+        d["mirrorsphere"] = {"type": "sphere", "to_world": _xf([T().scale(0.3), T().translate([0.0, -0.2, -0.5])], "mitsuba"),
+                             "bsdf": {"type": "ref", "id": "mirror"}}
+    desc = load_dict_desc(d)
     desc.source = "<builtin:furnace>"
     return desc
 

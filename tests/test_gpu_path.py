@@ -79,6 +79,26 @@ def test_furnace_closed_form(max_depth, rho, rr_depth, monkeypatch):
             assert np.abs(img - expect).max() <= 0.12 * expect                # every pixel, 256 spp
 
 
+def test_furnace_with_specular_spheres(monkeypatch):
+    """Glass + mirror spheres inside the furnace absorb nothing: 1 / (1 - rho) everywhere, also on and through the spheres
+    (pins the dielectric and conductor shading of both back ends to a closed form; three shading queues in play)."""
+    desc = scenes.furnace_scene(48, 256, max_depth=40, rho=0.5, rr_depth=5, spheres=True)
+    scene = mi.Scene(desc)
+    rp = scene.integrator().render_params(scene)
+    d1 = scenes.furnace_scene(48, 16, max_depth=1, rho=0.5, spheres=True)
+    s1 = mi.Scene(d1)
+    f1, _ = s1.device().render_path(s1.integrator().render_params(s1), seed=2, spp=16)
+    direct = _image(f1).mean(-1)
+    on_sphere, on_wall = direct < 0.02, direct > 0.98
+    assert on_sphere.sum() > 600 and on_wall.sum() > 800
+    for mode in ("wavefront", "mega"):
+        film, st = _render_mode(scene.device(), rp, mode, monkeypatch, seed=3, spp=256)
+        img = _image(film).mean(-1)
+        assert st["rays"] - st["shadow_rays"] == st["segments"]
+        assert abs(img[on_wall].mean() - 2.0) <= 0.004, (mode, img[on_wall].mean())
+        assert abs(img[on_sphere].mean() - 2.0) <= 0.015, (mode, img[on_sphere].mean())
+
+
 def test_render_sharded_equals_unsharded():
     desc = scenes.cbox_scene(48, 32)
     scene = mi.Scene(desc)

@@ -257,6 +257,30 @@ def test_path_tracer_oracle_furnace_closed_form(max_depth, rho, rr_depth):
         assert np.abs(img.mean((0, 1)) - expect).max() <= 6e-3 * expect          # per channel
 
 
+def test_path_tracer_oracle_furnace_with_specular_spheres():
+    """A glass and a mirror sphere inside the furnace absorb nothing: radiance stays 1 / (1 - rho) everywhere, on and
+    through the spheres too.  Pins the dielectric (Fresnel split, refraction, eta^2 bookkeeping) and conductor BSDFs of the
+    oracle's path tracer to a closed form."""
+    import orc_py
+    from prt_b200 import mi_compat as mi
+    desc = scenes.furnace_scene(24, 64, max_depth=40, rho=0.5, rr_depth=5, spheres=True)
+    sc = mi.Scene(desc)
+    rp = sc.integrator().render_params(sc)
+    osc = orc_py.OracleScene(desc)
+    film, st = orc_py.render_path(osc, rp, seed=1, spp=64, prec=32)
+    img = (film[..., :3] / film[..., 3:]).mean(-1)
+    assert st["misses"] == 0
+    assert abs(img.mean() - 2.0) <= 0.01
+    # which pixels look at a sphere: with max_depth = 1 only directly visible emission counts -- walls 1, spheres 0
+    d1 = scenes.furnace_scene(24, 16, max_depth=1, rho=0.5, spheres=True)
+    s1 = mi.Scene(d1)
+    f1, _ = orc_py.render_path(orc_py.OracleScene(d1), s1.integrator().render_params(s1), seed=2, spp=16, prec=32)
+    direct = (f1[..., :3] / f1[..., 3:]).mean(-1)
+    on_sphere, on_wall = direct < 0.02, direct > 0.98
+    assert on_sphere.sum() > 150 and on_wall.sum() > 200
+    assert abs(img[on_sphere].mean() - 2.0) <= 0.04 and abs(img[on_wall].mean() - 2.0) <= 0.01
+
+
 def test_pulse_shape_oracle_equals_the_prototype_echo_sum():
     """oracle/pyref.pulse_shape (checker of the f4 kernel) against the literal per-echo sum of RayTracingV0.py:193-201."""
     import pyref
