@@ -72,6 +72,9 @@ __device__ __forceinline__ void pt_apply_shadow(PtState &st, const ShadowReq &sr
 // something was hit).  Adds directly seen emission (MIS against emitter sampling at the previous vertex), draws the
 // emitter sample and reports it as a shadow-ray request, samples the BSDF, applies Russian roulette and writes the
 // next ray into st.  Returns false when the path is finished.
+// KSEL >= 0: the caller knows the material kind of every hit it passes (the wavefront's per-material shading kernels), so
+// the other materials' code -- and their registers -- drop out at compile time; KSEL < 0: read it from the material.
+template <int KSEL = -1>
 __device__ __forceinline__ bool pt_shade(const PtDev &P, PtState &st, const Hit &h, bool valid, ShadowReq &sr) {
     sr.want = false;
     const float3 md = -st.d;
@@ -80,7 +83,7 @@ __device__ __forceinline__ bool pt_shade(const PtDev &P, PtState &st, const Hit 
     float p0 = 0.0f, p1 = 1.0f;
     if (valid) {
         const DMaterial &m = P.sc.mats[h.material];
-        kind = __ldg(&m.kind);
+        kind = KSEL >= 0 ? KSEL : __ldg(&m.kind);
         p0 = __ldg(&m.p[0]);
         p1 = __ldg(&m.p[1]);
         refl_rgb = mk3(p0, p1, __ldg(&m.p[2]));

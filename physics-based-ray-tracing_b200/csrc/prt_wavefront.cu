@@ -79,6 +79,9 @@ enum { C_EXT = 0, C_MAT = 1, C_HEAD_EXT = 8, C_HEAD_SH = 12, C_SH = WF_CSTRIDE -
 // apart; evict-first hints (ld/st.global.cs) were meant to stop them displacing BVH nodes and triangles from L2.  Measured
 // on B200: no gain (height field 1 910 vs 1 932 Mrays/s, cbox 6 540 vs 6 577) -- L2's own replacement already keeps the
 // hot upper levels.  Left as a build knob, off.
+#ifndef WF_SHADE_KSEL
+#define WF_SHADE_KSEL 1                   // shading kernels 0 / 1 are compiled for their one material kind
+#endif
 #ifndef WF_SHADE_PREFETCH
 #define WF_SHADE_PREFETCH 0
 #endif
@@ -557,8 +560,11 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
 // ------------------------------------------------------------------------------------------------------------------
 // shading, one kernel per material queue
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef WF_SHADE0_MINB
+#define WF_SHADE0_MINB 3                  // the diffuse kernel is compiled without the other materials and fits 80 registers (32 B spill)
+#endif
 template <int QI>
-__global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(const PtDev P, const WfBuf B, const int bounce) {
+__global__ void __launch_bounds__(WF_SHADE_THREADS, QI == 0 ? WF_SHADE0_MINB : WF_SHADE_MINB) k_wf_shade(const PtDev P, const WfBuf B, const int bounce) {
     int *C = B.cnt + bounce * WF_CSTRIDE;
     static_assert(C_SH + 1 == WF_CSTRIDE && C_EXT == 0, "shadow count of bounce b must sit right below the extend count of bounce b + 1");
     // Two ways to find this kernel's paths.  The compacted queue (slot ids appended by the trace kernel, ballot +
@@ -617,7 +623,11 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MINB) k_wf_shade(co
             Hit h;
             if (id >= P.sc.n_prims) fill_tri_hit(P.sc, id - P.sc.n_prims, hv.x, hv.y, hv.z, h);
             else fill_prim_hit(P.sc.prims[id], id, st.o, st.d, hv.x, h);
+#if WF_SHADE_KSEL
+            live = pt_shade<QI == 0 ? PRT_MAT_DIFFUSE : (QI == 1 ? PRT_MAT_DIELECTRIC : -1)>(P, st, h, true, sr);
+#else
             live = pt_shade(P, st, h, true, sr);
+#endif
             wf_store_state(B, slot, st);
 #if WF_SLOT_SHADE
             if (!live) B.tag[slot] = 0;      // a live path's tag is rewritten when its next ray retires
