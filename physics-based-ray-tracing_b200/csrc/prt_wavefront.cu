@@ -689,7 +689,7 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
     PRT_REQUIRE(P.sc.n_tris == 0 || P.sc.n_nodes8 > 0, "render_path (wavefront): the scene has no 8-wide BVH");
     const uint32_t n_tiles = (uint32_t) P.tiles_x * (uint32_t) P.tiles_y;
     const uint64_t L = (uint64_t) n_tiles * 256u;
-    uint64_t batch = 1ull << 24;
+    uint64_t batch = 1ull << 25;      // 2^25 path slots = 11.7 GB of state + queues (measured: cbox +1 % over 2^24, -8 % at 2^22)
     if (const char *e = getenv("PRT_WF_BATCH")) {
         long long v = atoll(e);
         if (v > 0) batch = (uint64_t) v;
