@@ -46,6 +46,29 @@ def test_library_exports_every_declared_symbol():
     assert capi.SEG_DTYPE.itemsize == 32 + 4 * 8
 
 
+def test_ctypes_structs_match_the_header(tmp_path):
+    """Every struct capi.py mirrors has the size and field offsets the C compiler gives include/prt_b200.h (ABI drift guard)."""
+    pairs = {"prt_acq_params": capi.AcqParamsC, "prt_acq_stats": capi.AcqStatsC, "prt_bvh_stats": capi.BvhStatsC,
+             "prt_render_params": capi.RenderParamsC, "prt_render_stats": capi.RenderStatsC, "prt_das_params": capi.DasParamsC,
+             "prt_us_render_params": capi.UsRenderParamsC, "prt_kernel_times": capi.KernelTimesC}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "prt_b200.h")}"', "int main(void) {"]
+    for cname, ct in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  printf("prt_seg_record %zu\\n", sizeof(prt_seg_record));', "  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in pairs.items():
+        assert int(out[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(ct, fname).offset, (cname, fname)
+    assert int(out["prt_seg_record"]) == capi.SEG_DTYPE.itemsize
+
+
 def test_no_gpu_is_loud_not_a_fallback():
     """Without a CUDA device every compute entry point fails with a message; nothing computes on the CPU."""
     L = capi.load()
