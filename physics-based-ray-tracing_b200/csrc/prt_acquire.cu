@@ -32,6 +32,7 @@ struct AcqDev {
     uint64_t seed;
     uint32_t spp_total, s_offset, s_stride;
     uint64_t n_s, total;   // samples per (a,e) for this call, total paths of this call
+    int wae;               // 1: a warp's 32 lanes take 32 samples of ONE (angle, element) (identical primary rays); 0: 32 elements
     int a_first, a_count;  // angle range of this LAUNCH (prt_acquire pipelines one launch per angle with its D2H slice)
     unsigned long long var_mask;   // prt_acquire_variants: materials (bit = id) whose parameter is overridden in this launch
     int var_index;
@@ -171,6 +172,9 @@ __device__ __forceinline__ const DPrim *stage_prims(const DScene &sc, DPrim *sme
 // GPRIMS = true: more than MAX_SMEM_PRIMS analytic primitives, read from global memory.  Making that a template
 // parameter (instead of a run-time pointer choice) lets the compiler see that `prims` points into shared memory in the
 // common case and emit LDS instead of generic loads.
+#ifndef PRT_ACQ_WAE
+#define PRT_ACQ_WAE 1                     // warp-per-(angle, element) lane map: 0 off, 1 mesh scenes, 2 all scenes
+#endif
 #ifndef PRT_ACQ_DEFER
 #define PRT_ACQ_DEFER 1                   // mesh scenes: park continuing paths and run their segments in separate warp iterations
 #endif
@@ -200,9 +204,16 @@ __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const Acq
     const uint32_t ae0 = (uint32_t) P.a_first * (uint32_t) P.n_e;
     const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
     const uint64_t j0 = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t d_ae = (uint32_t) (stride % n_ae), d_si = (uint32_t) (stride / n_ae);
-    uint32_t ae = (uint32_t) (j0 % n_ae);
-    uint64_t si = j0 / n_ae;
+    // Two lane -> path maps.  Default: consecutive lanes take consecutive (angle, element) pairs at the same sample (their
+    // deposits fall into different rows).  P.wae (mesh scenes with >= 64 samples per pair): the 32 lanes of a warp take 32
+    // consecutive SAMPLES of one (angle, element) -- the reference's primary ray depends on the element only
+    // (CustomIntegrator.py:270-273), so the whole warp traverses the BVH with one and the same ray until the first hit.
+    const uint32_t lane_id = threadIdx.x & 31;
+    const uint64_t u0 = P.wae ? (j0 >> 5) : j0, du = P.wae ? (stride >> 5) : stride;
+    const uint32_t d_ae = (uint32_t) (du % n_ae), d_si = (uint32_t) (du / n_ae);
+    uint32_t ae = (uint32_t) (u0 % n_ae);
+    uint64_t sq = u0 / n_ae;                       // sample index, or block of 32 samples
+    uint64_t si = P.wae ? sq * 32 + lane_id : sq;
     // transmit-delay table, CI:87-94 / 254-257
     if (P.tx && j0 < n_ae) {
         uint32_t g = ae0 + (uint32_t) j0;
@@ -243,8 +254,9 @@ __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const Acq
             } else if (si < P.n_s) {
                 init_path(P, ae0 + ae, P.s_offset + (uint32_t) si * P.s_stride, ps);
                 ae += d_ae;
-                si += d_si;
-                if (ae >= n_ae) { ae -= n_ae; si++; }
+                sq += d_si;
+                if (ae >= n_ae) { ae -= n_ae; sq++; }
+                si = P.wae ? sq * 32 + lane_id : sq;
                 cn.paths++;
                 have = P.max_depth > 0;
             }
@@ -270,8 +282,9 @@ __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const Acq
                 if (si >= P.n_s) break;
                 init_path(P, ae0 + ae, P.s_offset + (uint32_t) si * P.s_stride, ps);
                 ae += d_ae;
-                si += d_si;
-                if (ae >= n_ae) { ae -= n_ae; si++; }
+                sq += d_si;
+                if (ae >= n_ae) { ae -= n_ae; sq++; }
+                si = P.wae ? sq * 32 + lane_id : sq;
                 cn.paths++;
                 live = P.max_depth > 0;
                 if (!live) continue;
@@ -357,6 +370,7 @@ static int fill_params(prt_scene *s, const prt_acq_params *p, uint64_t seed, uin
     P.total = P.n_s * (uint64_t) p->n_angles * (uint64_t) p->n_elements;
     P.a_first = 0;
     P.a_count = p->n_angles;
+    P.wae = 0;
     P.var_mask = 0ull;
     P.var_index = 0;
     P.var_value = 0.0f;
@@ -376,7 +390,9 @@ static int launch_acquire(prt_context *c, const AcqDev &P, cudaStream_t st) {
     PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACQ_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     const uint64_t n_ae_l = (uint64_t) P.a_count * P.n_e;
-    uint64_t want = (P.n_s * n_ae_l + ACQ_THREADS - 1) / ACQ_THREADS;
+    AcqDev Q = P;
+    Q.wae = (PRT_ACQ_WAE == 2 || (PRT_ACQ_WAE == 1 && tris)) && P.n_s >= 64;
+    uint64_t want = ((Q.wae ? (P.n_s + 31) / 32 * 32 : P.n_s) * n_ae_l + ACQ_THREADS - 1) / ACQ_THREADS;
     uint64_t n_ae_blocks = (n_ae_l + ACQ_THREADS - 1) / ACQ_THREADS;
     if (want < n_ae_blocks) want = n_ae_blocks;  // the tx-delay table is written by the first n_a*n_e threads
     uint64_t grid = (uint64_t) c->sm_count * per_sm;
@@ -384,7 +400,7 @@ static int launch_acquire(prt_context *c, const AcqDev &P, cudaStream_t st) {
     if (grid < 1) grid = 1;
     {
         ProfScope ps(c, PRT_KC_ACQUIRE, st);
-        kern<<<(unsigned) grid, ACQ_THREADS, 0, st>>>(P);
+        kern<<<(unsigned) grid, ACQ_THREADS, 0, st>>>(Q);
     }
     PRT_CUDA(cudaGetLastError());
     return PRT_OK;
