@@ -111,6 +111,12 @@ int prt_trace_occluded(prt_scene *, const float *o, const float *d, const float 
 int prt_ultra_bsdf_sample(prt_context *, uint64_t n, const float *wi, const float *ng, const float *ns,
                           const float *impedance, const float *roughness, const float *s1, const float *s2,
                           float *dir /*[n][3]*/, float *pdf, float *amp, int32_t *reflect);
+/* == directivity_weight_i(sec_dir, alpha_m, alpha_c) and directivity_weight_o(ray_dir, n, num_rays), the two nested
+ * functions of CustomIntegrator.py:114-135 / 286-304, on n explicit inputs (parity tests against tests/golden/
+ * ref_directivity.npz, which holds the outputs of the reference's own bytecode) */
+int prt_directivity_weights(prt_context *, uint64_t n, const double sensor_to_world[16], const float *sec_dir /*[n][3]*/,
+                            const float *ray_dir /*[n][3]*/, const float *normal /*[n][3]*/, double main_beam_deg,
+                            double cutoff_deg, double num_rays, float *w_i, float *w_o);
 
 /* ---- acquisition == UltraIntegrator.simulate_acquisition{,_parallel}(scene) --------------------
  * (CustomIntegrator.py:60-232, 235-405).  Property names / defaults: CustomIntegrator.py:16-42. */

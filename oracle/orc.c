@@ -379,15 +379,22 @@ int orc_scene_commit(orc_scene *s, int use_bvh) {
             if (ns) { ns[3 * i] = h.ns.x; ns[3 * i + 1] = h.ns.y; ns[3 * i + 2] = h.ns.z; }                        \
             if (wi) { wi[3 * i] = dot##SUF(md, h.fs); wi[3 * i + 1] = dot##SUF(md, h.ft);                          \
                       wi[3 * i + 2] = dot##SUF(md, h.ns); }                                                        \
+            if (fs) { fs[3 * i] = h.fs.x; fs[3 * i + 1] = h.fs.y; fs[3 * i + 2] = h.fs.z; }                        \
         }                                                                                                          \
     }
 
-int orc_trace_closest(const orc_scene *sc, int prec, const double *o, const double *d, const double *tmax, uint64_t n,
-                      double *t, int32_t *prim, int32_t *shape, double *p, double *ng, double *ns, double *wi) {
+int orc_trace_closest_frame(const orc_scene *sc, int prec, const double *o, const double *d, const double *tmax, uint64_t n,
+                            double *t, int32_t *prim, int32_t *shape, double *p, double *ng, double *ns, double *wi,
+                            double *fs) {
     if (prec == 32) { WRAP_CLOSEST(_f32, float) }
     else if (prec == 64) { WRAP_CLOSEST(_f64, double) }
     else return -1;
     return 0;
+}
+
+int orc_trace_closest(const orc_scene *sc, int prec, const double *o, const double *d, const double *tmax, uint64_t n,
+                      double *t, int32_t *prim, int32_t *shape, double *p, double *ng, double *ns, double *wi) {
+    return orc_trace_closest_frame(sc, prec, o, d, tmax, n, t, prim, shape, p, ng, ns, wi, NULL);
 }
 
 int orc_trace_occluded(const orc_scene *sc, int prec, const double *o, const double *d, const double *tmax, uint64_t n,
@@ -402,6 +409,49 @@ int orc_trace_occluded(const orc_scene *sc, int prec, const double *o, const dou
             v3_f64 dd = { d[3 * i], d[3 * i + 1], d[3 * i + 2] };
             hit[i] = (uint8_t) occluded_f64(sc, oo, dd, tmax ? tmax[i] : INFINITY, NULL);
         }
+    }
+    return 0;
+}
+
+int orc_ultra_bsdf_n(int prec, uint64_t n, const double *wi, const double *ng, const double *ns, const double *impedance,
+                     const double *roughness, const double *s1, const double *s2, double *dir, double *pdf, double *amp,
+                     int32_t *reflect) {
+    for (uint64_t i = 0; i < n; i++) {
+        int rc = orc_ultra_bsdf(prec, wi + 3 * i, ng + 3 * i, ns + 3 * i, impedance[i], roughness[i], s1[i], s2[i], dir + 3 * i,
+                                pdf + i, amp + i, reflect + i);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int orc_directivity(int prec, const double sensor_to_world[16], const double sec_dir[3], const double ray_dir[3],
+                    const double normal[3], double main_beam_deg, double cutoff_deg, double num_rays, double *w_i, double *w_o) {
+    orc_acq_params p;
+    memset(&p, 0, sizeof p);
+    memcpy(p.sensor_to_world, sensor_to_world, sizeof p.sensor_to_world);
+    p.main_beam_deg = main_beam_deg; p.cutoff_deg = cutoff_deg; p.n_angles = 1; p.n_elements = 1;
+    if (prec == 32) {
+        acq_f32 q; acq_setup_f32(&p, &q);
+        v3_f32 s = { (float) sec_dir[0], (float) sec_dir[1], (float) sec_dir[2] };
+        v3_f32 d = { (float) ray_dir[0], (float) ray_dir[1], (float) ray_dir[2] }, n = { (float) normal[0], (float) normal[1], (float) normal[2] };
+        *w_i = directivity_wi_f32(q.nT, s, q.alpha_m, q.alpha_c);
+        *w_o = dot_f32(d, n) / (float) num_rays;                     /* CI:117-118 */
+    } else if (prec == 64) {
+        acq_f64 q; acq_setup_f64(&p, &q);
+        v3_f64 s = { sec_dir[0], sec_dir[1], sec_dir[2] }, d = { ray_dir[0], ray_dir[1], ray_dir[2] }, n = { normal[0], normal[1], normal[2] };
+        *w_i = directivity_wi_f64(q.nT, s, q.alpha_m, q.alpha_c);
+        *w_o = dot_f64(d, n) / num_rays;
+    } else return -1;
+    return 0;
+}
+
+int orc_directivity_n(int prec, uint64_t n, const double *sensor_to_world /*[n][16]*/, const double *sec_dir, const double *ray_dir,
+                      const double *normal, const double *main_beam_deg, const double *cutoff_deg, const double *num_rays,
+                      double *w_i, double *w_o) {
+    for (uint64_t i = 0; i < n; i++) {
+        int rc = orc_directivity(prec, sensor_to_world + 16 * i, sec_dir + 3 * i, ray_dir + 3 * i, normal + 3 * i, main_beam_deg[i],
+                                 cutoff_deg[i], num_rays[i], w_i + i, w_o + i);
+        if (rc) return rc;
     }
     return 0;
 }

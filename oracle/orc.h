@@ -12,11 +12,19 @@
  * installed here, so their published algorithms are restated from the Mitsuba 3
  * sources as remembered.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this
- * path and cannot be executed in this image.  The oracle is pinned only against the
- * analytic anchors of SURVEY.md section 8(c) (tests/golden/anchors.json, generated by
- * tests/golden/make_anchors.py in exact/f64 arithmetic) and an independent pure-Python
- * transliteration (oracle/pyref.py).
+ * PINNING.  The reference ships no tests, golden vectors or fixtures, and Mitsuba cannot be installed here.  The
+ * oracle is pinned against
+ *   (1) fixtures produced by the reference's OWN Python: tests/golden/make_ref_fixtures.py executes
+ *       /root/reference/CustomBSDF.py and CustomIntegrator.py unmodified (on the repository's mitsuba / drjit stand-ins,
+ *       ray queries served by this oracle's intersector, uniforms injected from the per-path PCG32 streams) and records
+ *       12 000 UltraBSDF.sample calls, 4 000 directivity weights and 32 000 per-segment records of
+ *       simulate_acquisition / simulate_acquisition_parallel on ten scenes (tests/golden/ref_*.npz;
+ *       tests/test_ref_fixtures.py: every decision of every record reproduced exactly in binary32);
+ *   (2) the analytic anchors of SURVEY.md section 8(c) (tests/golden/anchors.json, exact / f64 arithmetic);
+ *   (3) an independent pure-Python transliteration (oracle/pyref.py) and an external PCG32 known-answer vector.
+ * STILL UNPINNED ("[MEM]"): what the reference obtains from the mitsuba wheel itself -- shape intersection routines,
+ * si.spawn_ray's offset, Frame3f / sh_frame / si.wi conventions, square_to_uniform_disk_concentric, TEA seeding, and the
+ * whole `path` integrator of orc_pt.inl (no reference code exists for it).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library.  The product (libprt_b200.so) never links or calls it.
@@ -112,12 +120,29 @@ int orc_scene_counts(const orc_scene *, int32_t *n_prims, int32_t *n_tris, int32
  * outputs may be NULL.  prim = -1, t = inf on miss. */
 int orc_trace_closest(const orc_scene *, int prec, const double *o, const double *d, const double *tmax, uint64_t n,
                       double *t, int32_t *prim, int32_t *shape, double *p, double *ng, double *ns, double *wi);
+/* same, plus the shading-frame tangent fs (si.sh_frame.s; t = n x s) the fixture harness needs to rebuild
+ * SurfaceInteraction3f for the reference's own Python (tests/golden/make_ref_fixtures.py) */
+int orc_trace_closest_frame(const orc_scene *, int prec, const double *o, const double *d, const double *tmax, uint64_t n,
+                            double *t, int32_t *prim, int32_t *shape, double *p, double *ng, double *ns, double *wi,
+                            double *fs);
 int orc_trace_occluded(const orc_scene *, int prec, const double *o, const double *d, const double *tmax, uint64_t n,
                        uint8_t *hit);
 
 /* == UltraBSDF.sample (CustomBSDF.py:87-175) on explicit inputs.  out: dir[3], pdf, amp, reflect */
 int orc_ultra_bsdf(int prec, const double wi[3], const double ng[3], const double ns[3], double impedance,
                    double roughness, double s1, double s2, double dir[3], double *pdf, double *amp, int32_t *reflect);
+
+/* == directivity_weight_i / directivity_weight_o (CustomIntegrator.py:114-135 / 286-304) on explicit inputs */
+int orc_directivity(int prec, const double sensor_to_world[16], const double sec_dir[3], const double ray_dir[3],
+                    const double normal[3], double main_beam_deg, double cutoff_deg, double num_rays, double *w_i, double *w_o);
+
+/* batched forms of the two (arrays of n) */
+int orc_ultra_bsdf_n(int prec, uint64_t n, const double *wi, const double *ng, const double *ns, const double *impedance,
+                     const double *roughness, const double *s1, const double *s2, double *dir, double *pdf, double *amp,
+                     int32_t *reflect);
+int orc_directivity_n(int prec, uint64_t n, const double *sensor_to_world /*[n][16]*/, const double *sec_dir, const double *ray_dir,
+                      const double *normal, const double *main_beam_deg, const double *cutoff_deg, const double *num_rays,
+                      double *w_i, double *w_o);
 
 /* == simulate_acquisition{,_parallel}.  Samples s = s_offset + j*s_stride < spp_total are traced for
  * every (angle, element); path index i = (a*n_e + e)*spp_total + s seeds PCG32 via sample_tea_32.

@@ -390,6 +390,13 @@ static inline R FN(elem_x)(const ACQ *q, int e) {
     return q->pitch * ((R) e - (R) (q->n_e - 1) * (R) 0.5);
 }
 
+/* directivity_weight_i, CI:120-135 / 289-304: alpha = |acos(dot(n_T, -sec_dir))|; 1 up to alpha_m, linear ramp to 0 at alpha_c */
+static inline R FN(directivity_wi)(V3 nT, V3 sec, R alpha_m, R alpha_c) {
+    R dt = FN(dot)(nT, FN(neg)(sec));                                /* CI:124-125 */
+    R al = FN(absr)(RACOS_FN(dt));                                   /* CI:126 */
+    return al <= alpha_m ? (R) 1 : (al <= alpha_c ? (alpha_c - al) / (alpha_c - alpha_m) : (R) 0); /* CI:128-133 */
+}
+
 /* One path, Appendix F.  buf may be NULL (trace-only); rec may be NULL. */
 static void FN(acq_path)(const orc_scene *sc, const ACQ *q, const orc_acq_params *p, uint64_t seed, uint32_t spp_total,
                          int a, int e, uint32_t s, double *buf, orc_seg_record *rec, orc_stats *st) {
@@ -436,9 +443,7 @@ static void FN(acq_path)(const orc_scene *sc, const ACQ *q, const orc_acq_params
         FN(ultra_bsdf)(wi, h.ng, h.ns, (R) mat->p[0], (R) mat->p[1], s1, s2, &dir, &pdf, &a_resp, &reflect); /* CI:175 / 338 */
         R cos_theta = FN(dot)(h.ns, md);                             /* CI:176 / 340 */
         amp *= a_resp * cos_theta * FN(maxr)(pdf, (R) 1e-6);         /* CI:177 / 341 (Q2) */
-        R dt = FN(dot)(q->nT, FN(neg)(sec));                         /* CI:124-125 */
-        R al = FN(absr)(RACOS_FN(dt));                               /* CI:126 */
-        R w_i = al <= q->alpha_m ? (R) 1 : (al <= q->alpha_c ? (q->alpha_c - al) / (q->alpha_c - q->alpha_m) : (R) 0); /* CI:128-133 */
+        R w_i = FN(directivity_wi)(q->nT, sec, q->alpha_m, q->alpha_c); /* CI:120-135 */
         R w_o = FN(dot)(d, h.ns) / q->n_rays;                      /* CI:118,184 (Q3) */
         R fd = w_i * w_o;
         R press = atten * amp * fd * RSIN_FN(phase);                 /* CI:187 / 348 */

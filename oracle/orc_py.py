@@ -2,7 +2,7 @@
 
 Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` / ``--impl reference`` legs
 may import this module.  The product package never does (its CUDA path fails loudly instead of
-falling back).  PARITY UNPINNED: see oracle/orc.h.
+falling back).  What the oracle is pinned on (and what stays [MEM]): see oracle/orc.h.
 """
 from __future__ import annotations
 
@@ -99,8 +99,12 @@ def lib():
         L.orc_scene_commit.argtypes = [C.c_void_p, C.c_int]
         L.orc_scene_counts.argtypes = [C.c_void_p, ip, ip, ip]
         L.orc_trace_closest.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, C.c_uint64, dp, ip, ip, dp, dp, dp, dp]
+        L.orc_trace_closest_frame.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, C.c_uint64, dp, ip, ip, dp, dp, dp, dp, dp]
         L.orc_trace_occluded.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, C.c_uint64, u8p]
         L.orc_ultra_bsdf.argtypes = [C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, dp, ip]
+        L.orc_directivity.argtypes = [C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, dp, dp]
+        L.orc_ultra_bsdf_n.argtypes = [C.c_int, C.c_uint64, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip]
+        L.orc_directivity_n.argtypes = [C.c_int, C.c_uint64, dp, dp, dp, dp, dp, dp, dp, dp, dp]
         L.orc_acquire.argtypes = [C.c_void_p, C.c_int, C.POINTER(AcqParamsC), C.c_uint64, C.c_uint32, C.c_uint32,
                                   C.c_uint32, dp, dp, C.POINTER(StatsC), C.c_int]
         L.orc_acquire_trace.argtypes = [C.c_void_p, C.c_int, C.POINTER(AcqParamsC), C.c_uint64, C.c_uint32, u64p,
@@ -212,13 +216,13 @@ class OracleScene:
         t = np.empty(n)
         prim = np.empty(n, dtype=np.int32)
         shape = np.empty(n, dtype=np.int32)
-        p, ng, ns, wi = (np.zeros((n, 3)) for _ in range(4))
+        p, ng, ns, wi, fs = (np.zeros((n, 3)) for _ in range(5))
         ip = C.POINTER(C.c_int32)
-        rc = self.L.orc_trace_closest(self.h, prec, _dptr(o), _dptr(d), _dptr(tm), n, _dptr(t), prim.ctypes.data_as(ip),
-                                      shape.ctypes.data_as(ip), _dptr(p), _dptr(ng), _dptr(ns), _dptr(wi))
+        rc = self.L.orc_trace_closest_frame(self.h, prec, _dptr(o), _dptr(d), _dptr(tm), n, _dptr(t), prim.ctypes.data_as(ip),
+                                            shape.ctypes.data_as(ip), _dptr(p), _dptr(ng), _dptr(ns), _dptr(wi), _dptr(fs))
         if rc:
             raise RuntimeError(f"orc_trace_closest failed: {rc}")
-        return dict(t=t, prim=prim, shape=shape, p=p, ng=ng, ns=ns, wi=wi)
+        return dict(t=t, prim=prim, shape=shape, p=p, ng=ng, ns=ns, wi=wi, sh_s=fs)
 
     def trace_occluded(self, o, d, tmax=None, prec: int = 32):
         o, d = _f64(o).reshape(-1, 3), _f64(d).reshape(-1, 3)
@@ -276,6 +280,40 @@ def ultra_bsdf(wi, ng, ns, impedance, roughness, s1, s2, prec=32):
     L.orc_ultra_bsdf(prec, _dptr(wi), _dptr(ng), _dptr(ns), impedance, roughness, s1, s2, _dptr(d), C.byref(pdf),
                      C.byref(amp), C.byref(rf))
     return d, pdf.value, amp.value, bool(rf.value)
+
+
+def ultra_bsdf_n(wi, ng, ns, impedance, roughness, s1, s2, prec=32):
+    """Batched ultra_bsdf: arrays of n -> (dir [n,3], pdf [n], amp [n], reflect [n] bool)."""
+    wi, ng, ns = _f64(wi).reshape(-1, 3), _f64(ng).reshape(-1, 3), _f64(ns).reshape(-1, 3)
+    n = wi.shape[0]
+    z, r, a, b = (_f64(np.broadcast_to(x, (n,))) for x in (impedance, roughness, s1, s2))
+    d, pdf, amp, rf = np.zeros((n, 3)), np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32)
+    rc = lib().orc_ultra_bsdf_n(prec, n, _dptr(wi), _dptr(ng), _dptr(ns), _dptr(z), _dptr(r), _dptr(a), _dptr(b), _dptr(d),
+                                _dptr(pdf), _dptr(amp), rf.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc:
+        raise RuntimeError("orc_ultra_bsdf_n failed")
+    return d, pdf, amp, rf.astype(bool)
+
+
+def directivity_n(sensor_to_world, sec_dir, ray_dir, normal, main_beam_deg, cutoff_deg, num_rays, prec=32):
+    sec, rd, nr = _f64(sec_dir).reshape(-1, 3), _f64(ray_dir).reshape(-1, 3), _f64(normal).reshape(-1, 3)
+    n = sec.shape[0]
+    T = _f64(np.broadcast_to(_f64(sensor_to_world).reshape(-1, 16), (n, 16)))
+    am, ac, nn = (_f64(np.broadcast_to(x, (n,))) for x in (main_beam_deg, cutoff_deg, num_rays))
+    wi, wo = np.zeros(n), np.zeros(n)
+    if lib().orc_directivity_n(prec, n, _dptr(T), _dptr(sec), _dptr(rd), _dptr(nr), _dptr(am), _dptr(ac), _dptr(nn), _dptr(wi), _dptr(wo)):
+        raise RuntimeError("orc_directivity_n failed")
+    return wi, wo
+
+
+def directivity(sensor_to_world, sec_dir, ray_dir, normal, main_beam_deg, cutoff_deg, num_rays, prec=32):
+    """(w_i, w_o) of CustomIntegrator.py:114-135 for one connection direction / one (ray direction, normal) pair."""
+    wi, wo = C.c_double(), C.c_double()
+    rc = lib().orc_directivity(prec, _dptr(_f64(sensor_to_world).reshape(16)), _dptr(_f64(sec_dir)), _dptr(_f64(ray_dir)),
+                               _dptr(_f64(normal)), float(main_beam_deg), float(cutoff_deg), float(num_rays), C.byref(wi), C.byref(wo))
+    if rc:
+        raise RuntimeError("orc_directivity failed")
+    return wi.value, wo.value
 
 
 def path_rng(seed: int, path: int):

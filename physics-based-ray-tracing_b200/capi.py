@@ -29,7 +29,7 @@ EXPORTS = [
     "prt_last_error", "prt_version", "prt_device_count", "prt_create", "prt_destroy", "prt_device_info", "prt_profile_begin", "prt_profile_read", "prt_host_alloc", "prt_host_free",
     "prt_scene_create", "prt_scene_destroy", "prt_scene_add_material", "prt_scene_set_material_param",
     "prt_scene_add_primitive", "prt_scene_add_mesh", "prt_scene_commit", "prt_trace_closest", "prt_trace_occluded",
-    "prt_ultra_bsdf_sample", "prt_acquire", "prt_acquire_dev", "prt_acquire_dev_angles", "prt_acquire_variants", "prt_acquire_trace", "prt_render_path",
+    "prt_ultra_bsdf_sample", "prt_directivity_weights", "prt_acquire", "prt_acquire_dev", "prt_acquire_dev_angles", "prt_acquire_variants", "prt_acquire_trace", "prt_render_path",
     "prt_render_path_dev", "prt_render_image", "prt_film_develop_dev", "prt_das_beamform", "prt_envelope", "prt_us_render", "prt_pulse_shape", "prt_pulse_shape_dev",
 ]
 
@@ -142,6 +142,7 @@ def load():
     L.prt_trace_closest.argtypes = [vp, fp, fp, fp, C.c_uint64, fp, ip, ip, fp, fp, fp, fp, fp]
     L.prt_trace_occluded.argtypes = [vp, fp, fp, fp, C.c_uint64, u8p]
     L.prt_ultra_bsdf_sample.argtypes = [vp, C.c_uint64, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, ip]
+    L.prt_directivity_weights.argtypes = [vp, C.c_uint64, dp, fp, fp, fp, C.c_double, C.c_double, C.c_double, fp, fp]
     L.prt_acquire.argtypes = [vp, C.POINTER(AcqParamsC), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, fp, fp,
                               C.POINTER(AcqStatsC)]
     L.prt_acquire_dev.argtypes = [vp, C.POINTER(AcqParamsC), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]

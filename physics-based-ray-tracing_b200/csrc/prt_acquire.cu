@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "prt_hit.cuh"
 #include "prt_internal.h"
@@ -127,12 +128,7 @@ __device__ __forceinline__ bool segment(const AcqDev &P, const DPrim *prims, Pat
         // CI:124-133: alpha = |acos(dot)|; w_i = 1 (alpha <= alpha_m), linear ramp to 0 at alpha_c, else 0.  acos is
         // monotone, so the two plateaus are decided on the cosine and acosf only runs on the ramp (rare: the aperture
         // subtends a few degrees; the ramp is continuous at both ends, so an ulp-level tie is immaterial)
-        const float cdt = dot(P.nT, -sec);
-        float w_i = cdt >= P.cos_m ? 1.0f : 0.0f;
-        if (cdt < P.cos_m && cdt >= P.cos_c) {
-            const float al = fabsf(acosf(cdt));
-            w_i = al <= P.alpha_m ? 1.0f : (al <= P.alpha_c ? (P.alpha_c - al) / (P.alpha_c - P.alpha_m) : 0.0f);
-        }
+        const float w_i = directivity_wi(P.nT, sec, P.cos_m, P.cos_c, P.alpha_m, P.alpha_c);
         const float w_o = dot(ps.d, h.ns) / P.n_rays;                            // CI:118,184
         press = ps.atten * ps.amp * (w_i * w_o) * sinf(phase);                   // CI:187 / 348
     }
@@ -334,8 +330,24 @@ static int fill_params(prt_scene *s, const prt_acq_params *p, uint64_t seed, uin
         float theta = (float) p->angles_deg[a] * (float) M_PI / 180.0f;
         sc[a] = make_float2(sinf(theta), cosf(theta));
     }
-    PRT_CUDA(cudaMemcpyAsync(c->angles_dev, sc.data(), sizeof(float2) * p->n_angles, cudaMemcpyHostToDevice, st));
-    PRT_CUDA(cudaStreamSynchronize(st));  // sc is a stack temporary
+    const float2 *table = nullptr;
+    for (const auto &t : c->angle_tables)
+        if (t.host.size() == sc.size() && !memcmp(t.host.data(), sc.data(), sizeof(float2) * sc.size())) { table = t.dev; break; }
+    if (!table) {           // first use of this set of angles: one synchronous upload, kept for the life of the context
+        if (c->angle_tables.size() >= 64) {
+            PRT_CUDA(cudaDeviceSynchronize());
+            for (auto &t : c->angle_tables) cudaFree(t.dev);
+            c->angle_tables.clear();
+        }
+        float2 *dev = nullptr;
+        PRT_CUDA(cudaMalloc((void **) &dev, sizeof(float2) * sc.size()));
+        cudaError_t e = cudaMemcpy(dev, sc.data(), sizeof(float2) * sc.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);    // pageable source: the DMA itself is ordered on the null stream
+        if (e != cudaSuccess) { cudaFree(dev); PRT_CUDA(e); }
+        c->angle_tables.push_back({sc, dev});
+        table = dev;
+    }
+    (void) st;
     const double *m = p->sensor_to_world;
     P.sc = s->view();
     P.T0 = make_float4((float) m[0], (float) m[1], (float) m[2], (float) m[3]);
@@ -361,7 +373,7 @@ static int fill_params(prt_scene *s, const prt_acq_params *p, uint64_t seed, uin
     P.Tn = p->time_samples;
     P.max_depth = p->max_depth;
     P.qf = p->quirk_flags;
-    P.sincos = reinterpret_cast<const float2 *>(c->angles_dev);
+    P.sincos = table;
     P.seed = seed;
     P.spp_total = spp_total;
     P.s_offset = s_offset;

@@ -530,6 +530,19 @@ __device__ __forceinline__ float3 spawn_origin(float3 p, float3 ng, float3 d) {
     return mk3(fmaf(ng.x, mag, p.x), fmaf(ng.y, mag, p.y), fmaf(ng.z, mag, p.z));
 }
 
+// directivity_weight_i (CustomIntegrator.py:120-135 / 289-304): alpha = |acos(dot(n_T, -sec))|; 1 for alpha <= alpha_m, linear
+// ramp to 0 at alpha_c, else 0.  acos is monotone, so the two plateaus are decided on the cosine and acosf only runs on the
+// ramp (rare: the aperture subtends a few degrees; the ramp is continuous at both ends, so an ulp-level tie is immaterial).
+__device__ __forceinline__ float directivity_wi(float3 nT, float3 sec, float cos_m, float cos_c, float alpha_m, float alpha_c) {
+    const float cdt = dot(nT, -sec);
+    float w_i = cdt >= cos_m ? 1.0f : 0.0f;
+    if (cdt < cos_m && cdt >= cos_c) {
+        const float al = fabsf(acosf(cdt));
+        w_i = al <= alpha_m ? 1.0f : (al <= alpha_c ? (alpha_c - al) / (alpha_c - alpha_m) : 0.0f);
+    }
+    return w_i;
+}
+
 // UltraBSDF.sample (CustomBSDF.py:87-175, _ggx_sample :30-61, ggx_pdf == 1 :81-82), SURVEY.md Appendix F.
 // All quirks Q4-Q9 are kept: scalar sample on the disk diagonal, mixed local/world frames, m flipped
 // against wi, "reflection" = wi + 2 (wi.m) m, local components returned as the new world direction.

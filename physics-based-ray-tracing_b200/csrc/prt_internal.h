@@ -68,6 +68,11 @@ struct prt_context {
     float    *aux_dev;   size_t aux_cap;      // tx_delays etc.
     uint64_t *stats_dev;                      // 8 x u64
     double   *angles_dev; size_t angles_cap;
+    // per-angle (sin, cos) tables of the acquisition, cached by CONTENT: a table is uploaded once, never overwritten while
+    // the context lives, so asynchronous launches on different streams can never see each other's angles and the *_dev entry
+    // points do no copy / stream synchronisation in steady state
+    struct AngleTable { std::vector<float2> host; float2 *dev; };
+    std::vector<AngleTable> angle_tables;
     void     *pinned;    size_t pinned_cap;   // pinned staging for D2H of results
     void     *wf_dev = nullptr; size_t wf_cap = 0;   // wavefront path-tracer state / queues (prt_wavefront.cu)
     int       last_launches = 0;              // kernels enqueued by the most recent render call

@@ -66,6 +66,15 @@ __global__ void k_ultra_bsdf(uint64_t n, const float *__restrict__ wi, const flo
     reflect[i] = rf ? 1 : 0;
 }
 
+__global__ void k_directivity(uint64_t n, float3 nT, float cos_m, float cos_c, float alpha_m, float alpha_c, float n_rays,
+                              const float *__restrict__ sec, const float *__restrict__ rd, const float *__restrict__ nrm,
+                              float *w_i, float *w_o) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    w_i[i] = directivity_wi(nT, mk3(sec[3 * i], sec[3 * i + 1], sec[3 * i + 2]), cos_m, cos_c, alpha_m, alpha_c);
+    w_o[i] = dot(mk3(rd[3 * i], rd[3 * i + 1], rd[3 * i + 2]), mk3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2])) / n_rays;   // CI:117-118
+}
+
 // small RAII pool of per-call device buffers
 struct DevBufs {
     std::vector<void *> ptrs;
@@ -170,6 +179,30 @@ int prt_ultra_bsdf_sample(prt_context *c, uint64_t n, const float *wi, const flo
     PRT_CUDA(cudaMemcpyAsync(pdf, pdf_d, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     PRT_CUDA(cudaMemcpyAsync(amp, amp_d, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     PRT_CUDA(cudaMemcpyAsync(reflect, rf_d, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    PRT_CUDA(cudaStreamSynchronize(st));
+    return PRT_OK;
+}
+
+int prt_directivity_weights(prt_context *c, uint64_t n, const double sensor_to_world[16], const float *sec_dir, const float *ray_dir,
+                            const float *normal, double main_beam_deg, double cutoff_deg, double num_rays, float *w_i, float *w_o) {
+    PRT_REQUIRE(c && sensor_to_world && sec_dir && ray_dir && normal && w_i && w_o, "prt_directivity_weights: null argument");
+    if (n == 0) return PRT_OK;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    PRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    // the same derived constants as fill_params (prt_acquire.cu): n_T = normalize(T (0,0,1)), radians, cosines
+    const float nx = (float) sensor_to_world[2], ny = (float) sensor_to_world[6], nz = (float) sensor_to_world[10];
+    const float nl = sqrtf(nx * nx + ny * ny + nz * nz);
+    const float3 nT = make_float3(nx / nl, ny / nl, nz / nl);
+    const float am = (float) (main_beam_deg * M_PI / 180.0), ac = (float) (cutoff_deg * M_PI / 180.0);
+    DevBufs b;
+    float *s_d, *r_d, *n_d, *wi_d, *wo_d;
+    TRY(b.upload(&s_d, sec_dir, 3 * n, st)); TRY(b.upload(&r_d, ray_dir, 3 * n, st)); TRY(b.upload(&n_d, normal, 3 * n, st));
+    TRY(b.alloc(&wi_d, n)); TRY(b.alloc(&wo_d, n));
+    k_directivity<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(n, nT, cosf(am), cosf(ac), am, ac, (float) num_rays, s_d, r_d, n_d, wi_d, wo_d);
+    PRT_CUDA(cudaGetLastError());
+    PRT_CUDA(cudaMemcpyAsync(w_i, wi_d, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    PRT_CUDA(cudaMemcpyAsync(w_o, wo_d, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     PRT_CUDA(cudaStreamSynchronize(st));
     return PRT_OK;
 }

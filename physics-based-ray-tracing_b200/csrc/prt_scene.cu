@@ -162,6 +162,7 @@ int prt_destroy(prt_context *c) {
     if (c->acc_dev) cudaFree(c->acc_dev);
     if (c->aux_dev) cudaFree(c->aux_dev);
     if (c->angles_dev) cudaFree(c->angles_dev);
+    for (auto &t : c->angle_tables) cudaFree(t.dev);
     if (c->stats_dev) cudaFree(c->stats_dev);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->wf_dev) cudaFree(c->wf_dev);

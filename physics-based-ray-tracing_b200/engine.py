@@ -266,6 +266,21 @@ def ultra_bsdf_sample(wi, ng, ns, impedance, roughness, s1, s2, context: Optiona
     return d, pdf, amp, rf.astype(bool)
 
 
+def directivity_weights(sensor_to_world, sec_dir, ray_dir, normal, main_beam_deg, cutoff_deg, num_rays,
+                        context: Optional[Context] = None):
+    """Batched directivity_weight_i / directivity_weight_o on the GPU (/root/reference/CustomIntegrator.py:114-135)."""
+    ctx = context or Context.get()
+    sec = np.ascontiguousarray(sec_dir, dtype=np.float32).reshape(-1, 3)
+    n = sec.shape[0]
+    rd = np.ascontiguousarray(np.broadcast_to(ray_dir, (n, 3)), dtype=np.float32)
+    nr = np.ascontiguousarray(np.broadcast_to(normal, (n, 3)), dtype=np.float32)
+    T = np.ascontiguousarray(sensor_to_world, dtype=np.float64).reshape(16)
+    w_i, w_o = np.empty(n, dtype=np.float32), np.empty(n, dtype=np.float32)
+    check(ctx.L.prt_directivity_weights(ctx.h, n, dptr(T), fptr(sec), fptr(rd), fptr(nr), float(main_beam_deg), float(cutoff_deg),
+                                        float(num_rays), fptr(w_i), fptr(w_o)), "prt_directivity_weights")
+    return w_i, w_o
+
+
 def das_beamform(channel, angles_deg, x, z, fs, sound_speed, pitch, t0=0.0, f_number=0.0, tx_delays=None,
                  context: Optional[Context] = None):
     """Plane-wave delay-and-sum + envelope on the GPU (replaces ultraspy's DelayAndSum, USMain.py:175-208).
