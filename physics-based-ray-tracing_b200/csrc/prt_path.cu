@@ -94,6 +94,142 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_render_path(const PtDev P) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Resident-scene kernel: scenes whose geometry fits shared memory (scenes/cbox.xml: 2 analytic spheres + 12 triangles).
+//
+// For such a scene the wavefront pipeline spends more than half of its step streaming path state and ray records through
+// HBM (profiles/r01: shade + generate + film = 53 % of the cbox step, 380 B per segment) around ray queries that touch
+// 2 KB of geometry.  Here nothing leaves the SM: the analytic primitives AND the triangles are staged in shared memory
+// and tested by brute force (no tree, no stack, uniform control flow across the warp), path state lives in registers,
+// and the only global traffic is the finished 16 x 16 film tile.  Unlike k_render_path, work inside a tile is handed out
+// dynamically: the tile's (sample, pixel) items are numbered s * 256 + pixel-in-tile (32 consecutive items = one 8 x 4
+// pixel block of one sample, so primary rays stay coherent) and a lane whose path ends takes the next item from a
+// shared-memory counter, whichever pixel it belongs to -- a thread that drew long paths no longer holds its warp and its
+// CTA back (with 16 samples per pixel the fixed pixel -> thread map left ~25 % of the lane-iterations idle).
+// Same pt_init / pt_shade, same per-path PCG32 streams: identical paths, identical radiance per path.
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int PT_RES_MAX_TRIS = 64;
+#ifndef PT_RES_MINB
+#define PT_RES_MINB 3
+#endif
+
+struct ResScene {
+    const DPrim *prims;      // shared memory
+    const float4 *tv;        // shared memory: [n_tris][3] vertices, sorted order (v1.w unused here)
+    int n_prims, n_tris;
+};
+
+__device__ __forceinline__ bool res_closest(const PtDev &P, const ResScene &R, float3 o, float3 d, Hit &h) {
+    int best = -1, tri = -1;
+    float tb = PRT_INF, b1 = 0.0f, b2 = 0.0f;
+    for (int i = 0; i < R.n_prims; i++) {
+        const float t = intersect_prim(R.prims[i], o, d, tb);
+        if (t >= 0.0f && (best < 0 || t < tb)) { best = i; tb = t; }
+    }
+    const RayRows rr = ray_rows(ray_precompute(d));
+    for (int j = 0; j < R.n_tris; j++) {
+        const float4 *tv = R.tv + 3 * j;
+        if (intersect_tri_rows(rr, o, xyz(tv[0]), xyz(tv[1]), xyz(tv[2]), tb, b1, b2)) tri = j;
+    }
+    if (tri >= 0) { fill_tri_hit(P.sc, tri, tb, b1, b2, h); return true; }
+    if (best < 0) return false;
+    fill_prim_hit(R.prims[best], best, o, d, tb, h);
+    return true;
+}
+
+__device__ __forceinline__ bool res_occluded(const ResScene &R, float3 o, float3 d, float tmax) {
+    for (int i = 0; i < R.n_prims; i++)
+        if (intersect_prim(R.prims[i], o, d, tmax) >= 0.0f) return true;
+    const RayRows rr = ray_rows(ray_precompute(d));
+    float tb = tmax, b1, b2;
+    for (int j = 0; j < R.n_tris; j++) {
+        const float4 *tv = R.tv + 3 * j;
+        if (intersect_tri_rows(rr, o, xyz(tv[0]), xyz(tv[1]), xyz(tv[2]), tb, b1, b2)) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(PT_THREADS, PT_RES_MINB) k_render_resident(const PtDev P) {
+    __shared__ DPrim sprims[MAX_SMEM_PRIMS];
+    __shared__ float4 stri[3 * PT_RES_MAX_TRIS];
+    __shared__ float4 tile[PT_HALO * PT_HALO];
+    __shared__ unsigned s_next;
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(P.sc.prims);
+        float4 *dst = reinterpret_cast<float4 *>(sprims);
+        for (int i = threadIdx.x; i < P.sc.n_prims * (int) (sizeof(DPrim) / 16); i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < 3 * P.sc.n_tris; i += blockDim.x) stri[i] = P.sc.tri_v[i];
+    }
+    ResScene R;
+    R.prims = sprims; R.tv = stri; R.n_prims = P.sc.n_prims; R.n_tris = P.sc.n_tris;
+    const int lane = threadIdx.x & 31;
+    PtCounters cn = { 0, 0, 0, 0 };
+    const int n_tiles = P.tiles_x * P.tiles_y;
+    const unsigned n_items = P.n_s * 256u;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int tx0 = (t % P.tiles_x) * PT_TILE, ty0 = (t / P.tiles_x) * PT_TILE;
+        for (int i = threadIdx.x; i < PT_HALO * PT_HALO; i += blockDim.x) tile[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (threadIdx.x == 0) s_next = 0u;
+        __syncthreads();
+        PtState st;
+        bool live = false, dry = false;      // dry: warp-uniform
+        for (;;) {
+            if (!dry) {
+                const unsigned need = __ballot_sync(0xffffffffu, !live);
+                if (need) {
+                    unsigned base = 0u;
+                    if (lane == __ffs(need) - 1) base = atomicAdd(&s_next, (unsigned) __popc(need));
+                    base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+                    if (!live) {
+                        const unsigned item = base + __popc(need & ((1u << lane) - 1u));
+                        if (item < n_items) {
+                            const unsigned j = item >> 8, r = item & 255u, w = r >> 5, l = r & 31u;
+                            const int x = tx0 + (int) ((w & 1u) * 8u + (l & 7u)), y = ty0 + (int) ((w >> 1) * 4u + (l >> 3));
+                            if (x < P.W && y < P.H) {
+                                pt_init(P, x, y, P.s_offset + j * P.s_stride, st);
+                                cn.paths++;
+                                live = true;
+                            }
+                        }
+                    }
+                    dry = base + (unsigned) __popc(need) >= n_items;
+                }
+            }
+            if (!__any_sync(0xffffffffu, live)) {
+                if (dry) break;
+                continue;
+            }
+            if (live) {
+                Hit h;
+                cn.rays++;
+                const bool valid = res_closest(P, R, st.o, st.d, h);
+                if (valid) cn.segments++;
+                ShadowReq sr;
+                live = pt_shade(P, st, h, valid, sr);
+                if (sr.want) {
+                    cn.rays++;
+                    cn.shadow++;
+                    if (!res_occluded(R, sr.o, sr.d, sr.tmax)) pt_apply_shadow(st, sr);
+                }
+                if (!live) pt_splat(P.tent, tile, tx0, ty0, st.px, st.py, st.res);
+            }
+        }
+        __syncthreads();
+        pt_flush_tile(P, tile, tx0, ty0);
+        __syncthreads();
+    }
+    if (P.stats) {
+        unsigned v[4] = { cn.paths, cn.segments, cn.rays, cn.shadow };
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            unsigned xx = v[q];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) xx += __shfl_xor_sync(0xffffffffu, xx, o);
+            if (lane == 0 && xx) atomicAdd(P.stats + q, (unsigned long long) xx);
+        }
+    }
+}
+
 // hdrfilm develop (scenes/cbox.xml:25-31): rgb = sum(w c) / sum(w); pixels no sample reached stay 0
 __global__ void __launch_bounds__(256) k_film_develop(const float4 *__restrict__ film, uint64_t n_pixels, float *__restrict__ rgb) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_pixels; i += (uint64_t) gridDim.x * blockDim.x) {
@@ -157,18 +293,27 @@ static int launch_pt(prt_context *c, const PtDev &P, cudaStream_t st) {
     // fetch) is the default: measured on B200 it beats this tile megakernel on both bench scenes (cbox 5.3 vs 3.6
     // Grays/s, 10 M-triangle height field 1.14 vs 0.67), because per-ray traversal length is heavy-tailed and the
     // megakernel idles the lanes of a warp behind its longest ray.  PRT_PT_MODE=mega|wavefront overrides.
+    // PRT_PT_MODE=mega|wavefront|resident overrides.  Default: scenes whose geometry fits shared memory (<= 64 analytic
+    // primitives, <= 64 triangles) run in the resident-scene kernel; everything else in the wavefront pipeline.
     const char *mode = getenv("PRT_PT_MODE");
-    bool wavefront = !(mode && mode[0] == 'm');
-    if (wavefront) return launch_wavefront(c, P, st);
+    const bool fits = P.sc.n_prims <= MAX_SMEM_PRIMS && P.sc.n_tris <= PT_RES_MAX_TRIS;
+    int which = fits ? 2 : 1;                      // 0 tile megakernel, 1 wavefront, 2 resident
+    if (mode && mode[0] == 'm') which = 0;
+    else if (mode && mode[0] == 'w') which = 1;
+    else if (mode && mode[0] == 'r') which = 2;
+    if (which == 2 && !fits) { set_error("render_path: PRT_PT_MODE=resident needs <= 64 primitives and <= 64 triangles"); return PRT_ERR_INVALID; }
+    if (which == 1) return launch_wavefront(c, P, st);
+    const void *kern = which == 2 ? (const void *) k_render_resident : (const void *) k_render_path;
     int per_sm = 0;
-    PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_path, PT_THREADS, 0));
+    PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PT_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     int grid = c->sm_count * per_sm;
     int n_tiles = P.tiles_x * P.tiles_y;
     if (grid > n_tiles) grid = n_tiles;
     {
         ProfScope ps(c, PRT_KC_MEGAKERNEL, st);
-        k_render_path<<<grid, PT_THREADS, 0, st>>>(P);
+        if (which == 2) k_render_resident<<<grid, PT_THREADS, 0, st>>>(P);
+        else k_render_path<<<grid, PT_THREADS, 0, st>>>(P);
     }
     PRT_CUDA(cudaGetLastError());
     c->last_launches = 1;
