@@ -1,19 +1,28 @@
 #!/usr/bin/env python3
-"""bench.py -- headline benchmark of the acquisition hot path (BASELINE.json metric: Mrays/s & Msamples/s).
+"""bench.py -- benchmark of the ray-traced acquisition / path-tracing hot path (BASELINE.json metric: Mrays/s & Msamples/s).
 
-  python bench.py --gpus N --steps K --warmup W [--workload sphere_box|ring|...] [--impl reference]
+  python bench.py --gpus N --steps K --warmup W [--workload W] [--also a,b,...|none] [--impl reference]
 
-One "step" = one pass of the hot path over one batch: a full acquisition of the workload's scene with
-BASELINE.json config 2's path count (512*512*256 = 67 108 864 paths -> 5 angles x 64 elements x 209 716
-samples) per GPU (weak scaling: rank g traces samples g, g+N, ... of N x 209 716, then ONE NCCL
-all-reduce of the 12.8 MB channel buffer).  `value` = Mrays/s with everything resident in HBM (device
-buffers, CUDA-event timed, max over ranks); `e2e` = the same metric through the reference-facing plugin
-call `UltraIntegrator.simulate_acquisition_parallel(scene)` with HOST (numpy) results, i.e. including the
-zero-fill, the D2H copy of the channel buffer and its hand-over to numpy.
+ONE JSON line on stdout.  Headline workload (`config.workload`): BASELINE.json config 2 on MitsubaScenes/Sphere_Box.xml with
+the transducer looking AT the sphere ("intended" transform order, the composition the reference's own dict scene uses,
+USMain.py:69-71): 5 angles x 64 elements x 209 716 samples = 67 109 120 paths per step and GPU, multi-bounce, non-zero
+deposits.  (Under Mitsuba's left-multiplying XML rule the array sits INSIDE the sphere, every connection is occluded and the
+channel buffer is identically zero -- SURVEY.md Q1; that degenerate case is kept as the `sphere_box` entry of `also`.)
 
-`--impl reference` times the reference's CPU path -- the C restatement in oracle/ ("port": the real
-reference needs mitsuba/drjit, which cannot be installed here) -- on all host cores, on a bounded sample
-(BASELINE.json config 1: 1 048 640 paths per step) of the same workload.
+One "step" = one complete acquisition (weak scaling: rank g traces samples g, g+N, ... of N x 209 716, then ONE NCCL sum
+all-reduce of the 12.8 MB channel buffer, issued per steering-angle slice so that it overlaps the next angle's kernel).
+  value     Mrays/s, everything resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e       the same metric through the reference-facing plugin call UltraIntegrator.simulate_acquisition_parallel(scene)
+            returning a HOST numpy buffer (zero-fill, kernels, all-reduce, D2H inside the timed region)
+  roofline  of the dominant kernel, timed live inside the library with CUDA events (prt_profile_begin/read).  Scenes that
+            live on chip are bound by instruction issue: achieved = warp instructions/s (per-ray count from the committed
+            ncu capture x this run's rays/s), peak = 4 schedulers x 148 SMs x the SM clock sampled during the run; the
+            DRAM-traffic view is reported beside it (`hbm`).  Only the 10 M-triangle scene is HBM-bound (`bound: "hbm"`).
+  also      the other BASELINE configs, measured briefly in the same job at the same N (compact entries, last in the line):
+            sphere_box (Mitsuba rule, degenerate), ring (config 3), cbox (config 4), heightfield (config 5)
+  cpu_baseline / --impl reference: the C restatement of the reference path (oracle/, kind "port": the real reference needs
+            mitsuba/drjit, not installable here) on all host threads.  --impl reference traces the SAME job per step as the
+            GPU arm (same `config`); cpu_baseline inside the GPU arm is a bounded ~10 s sample of it.
 """
 from __future__ import annotations
 
@@ -34,6 +43,13 @@ import numpy as np  # noqa: E402
 
 C2_SPP = 209716          # ceil(512*512*256 / 320): BASELINE.json config 2 as (angle, element, sample) paths
 C1_SPP = 3277            # ceil(256*256*16 / 320):  BASELINE.json config 1 (the reference's CPU-runnable case)
+DEFAULT_WORKLOAD = "sphere_box:intended"
+DEFAULT_ALSO = "sphere_box,ring,cbox,heightfield"
+N_SM, SCHEDULERS = 148, 4
+
+
+def is_pt(name: str) -> bool:
+    return name == "cbox" or name.startswith("heightfield")
 
 
 def workload_desc(name: str):
@@ -47,6 +63,15 @@ def workload_desc(name: str):
         raise SystemExit(f"unknown workload {name!r}")
     order = order or "mitsuba"
     return scenes.ultrasound_scene(table[base], order), f"MitsubaScenes/{table[base]}.xml ({order} transform order)"
+
+
+def acq_config(label, p, spp, world, n_tris, n_analytic):
+    """The `config` object of an acquisition workload -- built identically by the GPU arm and by --impl reference."""
+    return {"workload": label, "paths_per_gpu_per_step": int(p.n_angles * p.n_elements * spp), "spp_per_gpu": int(spp),
+            "n_angles": int(p.n_angles), "n_elements": int(p.n_elements), "time_samples": int(p.time_samples),
+            "max_depth": int(p.max_depth), "n_triangles": int(n_tris), "n_analytic": int(n_analytic),
+            "parallelism": f"sample-shards x{world}, scene replicated, one sum all-reduce of the channel buffer per step",
+            "l2": "flushed between timed steps (384 MiB fill, untimed); inputs are < 200 KB and live on chip by design"}
 
 
 class ClockSampler:
@@ -111,6 +136,48 @@ def bvh_min_bytes(n_tris: int) -> int:
     return int(np.ceil(np.log2(max(n_tris / 4.0, 1.0)))) * 64 + 4 * 48 + 48
 
 
+def ncu_entry(key: str) -> dict:
+    """What the committed `ncu --set full` capture of this workload's dominant kernel says (profiles/traffic.json):
+    DRAM bytes per launch, warp instructions per ray, issue-slot utilisation.  {} if not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as fh:
+        d = json.load(fh)
+    return d.get(key) or d.get(key.partition(":")[0], {}) if not key.startswith("heightfield") else d.get("heightfield", {})
+
+
+def roofline_block(workload, kernel, launch_ms, rays_per_launch, alg_bytes, clk, on_chip: bool):
+    """roofline for the dominant kernel.  on_chip: bound by instruction issue (frac never exceeds 1: achieved is an
+    instruction rate against the issue peak); else HBM.  The DRAM-traffic view sits beside it in either case."""
+    peak_hbm, peak_src, sm_max = measured_peaks()
+    e = ncu_entry(workload)
+    traffic = e.get("dram_bytes_per_launch") if e.get("kernel", kernel) == kernel else None
+    sec = launch_ms * 1e-3
+    hbm = {"algorithmic_gbs": alg_bytes / sec / 1e9, "peak_gbs": peak_hbm, "peak_source": peak_src}
+    if traffic is not None:
+        # traffic of the captured launch scaled to this run's launch by the ray count
+        scale = rays_per_launch / e["rays_per_launch"] if e.get("rays_per_launch") else 1.0
+        hbm["dram_gbs"] = traffic * scale / sec / 1e9
+        hbm["dram_frac"] = hbm["dram_gbs"] / peak_hbm
+    if on_chip:
+        mhz = (clk or {}).get("sm_mhz") or sm_max
+        peak = N_SM * SCHEDULERS * mhz * 1e6 / 1e9
+        wipr = e.get("warp_inst_per_ray") if e.get("kernel", kernel) == kernel else None
+        ach = rays_per_launch * wipr / sec / 1e9 if wipr else None
+        frac = ach / peak if ach else None
+        rf = {"bound": "issue", "achieved": ach, "peak": peak, "unit": "Gwarp-inst/s", "frac": frac, "traffic": traffic,
+              "warp_inst_per_ray": wipr, "ncu_issue_active_pct": e.get("issue_active_pct"),
+              "ncu_active_lanes": e.get("active_threads_per_warp"), "source": e.get("source"), "hbm": hbm}
+        if frac is not None and frac > 1.0:      # a stale per-ray instruction count: not evidence of anything
+            rf.update(frac=None, achieved=None, stale=True)
+        return rf
+    ach = alg_bytes / sec / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm, "traffic": traffic,
+            "algorithmic_bytes_per_launch": alg_bytes, "ncu_issue_active_pct": e.get("issue_active_pct"),
+            "ncu_active_lanes": e.get("active_threads_per_warp"), "source": e.get("source"), "hbm": hbm}
+
+
 def cpu_oracle_rate(desc, params, spp: int, seed: int, threads: int):
     import orc_py
     sc = orc_py.OracleScene(desc)
@@ -120,46 +187,182 @@ def cpu_oracle_rate(desc, params, spp: int, seed: int, threads: int):
     return st, dt
 
 
-def ncu_entry(key: str) -> dict:
-    """What the committed `ncu --set full` capture of this workload's dominant kernel says (profiles/traffic.json,
-    transcribed from profiles/*_ncu_*.txt): DRAM bytes per launch, warp instructions per ray.  {} if not captured."""
-    path = os.path.join(ROOT, "profiles", "traffic.json")
-    if not os.path.exists(path):
-        return {}
-    with open(path) as fh:
-        return json.load(fh).get(key.partition(":")[0] if key.startswith("heightfield") else key, {})
+def cpu_acq_baseline(desc, p, seconds: float, extra_legs: bool):
+    """Bounded sample of the same workload on all host threads (+ the single-thread / pure-Python legs of SURVEY 8(d))."""
+    threads = os.cpu_count() or 1
+    n_ae = p.n_angles * p.n_elements
+    st, dt = cpu_oracle_rate(desc, p, C1_SPP, 0, threads)
+    reps = int(min(max(seconds / max(dt, 1e-3), 1), 2000))
+    rays_c, t_c = st["rays"], dt
+    for k in range(1, reps):
+        st, dt = cpu_oracle_rate(desc, p, C1_SPP, k, threads)
+        rays_c += st["rays"]; t_c += dt
+    out = {"value": rays_c / t_c / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+           "sample": f"{reps} x {C1_SPP * n_ae} paths of the same scene (BASELINE config 1 path count), oracle f32, {threads} threads, {t_c:.1f} s"}
+    if extra_legs:
+        st1, dt1 = cpu_oracle_rate(desc, p, C1_SPP, 0, 1)
+        out["single_thread"] = {"value": st1["rays"] / dt1 / 1e6, "unit": "Mrays/s", "cores": 1}
+        try:
+            import pyref
+            shapes_py = pyref.shapes_from_desc(desc)
+            t0 = time.perf_counter()
+            _, _, stp = pyref.acquire(shapes_py, p, seed=0, spp=1)
+            dtp = time.perf_counter() - t0
+            out["pure_python"] = {"value": stp["rays"] / dtp / 1e6, "unit": "Mrays/s", "cores": 1,
+                                  "sample": f"{n_ae} paths (the reference's literal acquisition), oracle/pyref.py"}
+        except ValueError:
+            pass                         # pyref handles sphere / rectangle scenes only
+    return out
 
 
-def ncu_traffic(key: str):
-    e = ncu_entry(key)
-    return (e.get("dram_bytes_per_launch"), e.get("source")) if e else (None, None)
-
-
-WF_RAY_RECORD_BYTES = 64 + 16      # ray record read (4 x float4) + hit record written, per closest-hit query
-
-
-def pt_measure(args, workload, steps, warmup, rank, world, device, e2e_steps, cpu_baseline):
-    """One path-tracing workload (cbox = BASELINE config 4, heightfield = config 5) on an initialised process group.
-    One step = one batch of `spp` samples per pixel per GPU (the 4096-spp job is 256 such steps at 16 spp).
-    Returns the JSON line (rank 0) or None."""
+# ----------------------------------------------------------------------------------------------------------------------
+# acquisition workloads (BASELINE configs 2 and 3)
+# ----------------------------------------------------------------------------------------------------------------------
+def acq_measure(args, workload, steps, warmup, rank, world, device, e2e_steps, cpu_seconds, extra_legs=False):
     import torch
     import torch.distributed as dist
     from prt_b200 import mi_compat as mi
+    from prt_b200.distributed import acquire_allreduce_pipelined, shard_samples
+
+    desc, label = workload_desc(workload)
+    scene = mi.Scene(desc)
+    integ = scene.integrator()
+    dev = scene.device()
+    p = integ.acq_params(scene)
+    n_ae = p.n_angles * p.n_elements
+    spp_total = args.spp * world                       # weak scaling: per-GPU work fixed
+    off, stride, n_s = shard_samples(spp_total, rank, world)
+    buf = torch.zeros((p.n_angles, p.n_elements, p.time_samples), dtype=torch.float32, device=device)
+    tx = torch.zeros((p.n_angles, p.n_elements), dtype=torch.float32, device=device)
+    stats = torch.zeros(8, dtype=torch.int64, device=device)
+    flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=device)   # > 126 MB L2
+    stream = torch.cuda.current_stream(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for w in range(warmup):
+        buf.zero_()
+        acquire_allreduce_pipelined(dev, p, buf, tx, stats, stream, 1000 + w, spp_total, off, stride, dist, world)
+    barrier()
+    stats.zero_()
+    clocks = ClockSampler(device.index)
+    clocks.start()
+    time.sleep(0.4)                                 # let nvidia-smi start sampling before the timed region
+    ev = []
+    barrier()
+    dev.ctx.profile_begin()                         # event pair around every k_acquire launch, on the launching stream
+    for k in range(steps):
+        flush.fill_(k & 0xff)                       # L2 flush between timed iterations (untimed)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record(stream)
+        buf.zero_()
+        acquire_allreduce_pipelined(dev, p, buf, tx, stats, stream, k, spp_total, off, stride, dist, world)
+        e[1].record(stream)
+        ev.append(e)
+    barrier()
+    clk = clocks.stop()
+    classes = dev.ctx.profile_read()
+    t_local = torch.tensor([sum(e[0].elapsed_time(e[1]) for e in ev)], dtype=torch.float64, device=device)
+    checksum_dev = float(buf.abs().sum().item())
+    st_local = stats.cpu().numpy().copy()
+    st_all = stats.clone()
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+        dist.all_reduce(st_all, op=dist.ReduceOp.SUM)
+    total_ms = float(t_local.item())
+    hs = st_all.cpu().numpy()
+    paths, segments, rays, deposits = int(hs[0]), int(hs[1]), int(hs[2]), int(hs[3])
+    value = rays / (total_ms * 1e-3) / 1e6
+
+    # ---- end to end through the reference-facing plugin call, HOST results -----------------------------------
+    integ.samples_per_element = spp_total
+    integ.seed = 999
+    so = sys.stdout
+    sys.stdout = open(os.devnull, "w")               # the reference's method prints; keep ONE JSON line on stdout
+    try:
+        integ.simulate_acquisition_parallel(scene)  # warm-up (allocates the pinned result buffers: the pool needs
+        integ.simulate_acquisition_parallel(scene)  # two, because the integrator still holds the previous result)
+        barrier()
+        e2e_rays = 0
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            integ.seed = 2000 + k
+            integ.simulate_acquisition_parallel(scene)
+            e2e_rays += int(integ.last_stats["rays"])
+            host_checksum = float(np.abs(integ.channel_buf.ravel()[::997]).sum())   # touch the HOST result
+        barrier()
+        e2e_dt = time.perf_counter() - t0
+    finally:
+        sys.stdout.close()
+        sys.stdout = so
+    t_e2e = torch.tensor([e2e_dt], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)   # acquire_sharded reduces the stats: every rank holds the global ray count
+    e2e_value = e2e_rays / float(t_e2e.item()) / 1e6
+    del flush
+    if rank != 0:
+        return None
+    n_tris = desc.n_triangles()
+    acq = classes.get("acquire") or {"ms": total_ms, "launches": steps}
+    launch_ms = acq["ms"] / max(acq["launches"], 1)
+    rays_per_launch = int(st_local[2]) / max(acq["launches"], 1)
+    # algorithmic bytes per launch (DESIGN.md section 5): BVH descent per ray (0 for analytic scenes, which live in shared
+    # memory) + this launch's slice of the channel buffer written once (no per-segment state is streamed)
+    alg_bytes = rays_per_launch * bvh_min_bytes(n_tris) + buf.numel() * 4 * steps / max(acq["launches"], 1)
+    kernel = "prt::k_acquire<%s>" % ("true" if n_tris else "false")
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "msamples_per_s": paths / (total_ms * 1e-3) / 1e6, "msegments_per_s": segments / (total_ms * 1e-3) / 1e6,
+        "config": acq_config(label, p, args.spp, world, n_tris, desc.n_analytic()),
+        "segments_per_path": segments / max(paths, 1), "rays_per_path": rays / max(paths, 1),
+        "deposits_per_path": deposits / max(paths, 1), "device_checksum": checksum_dev,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(8 * p.n_angles + 512),
+                "d2h_bytes_per_step": int(buf.numel() * 4 + tx.numel() * 4 + 64), "steps": e2e_steps,
+                "api": "UltraIntegrator.simulate_acquisition_parallel(scene) -> numpy channel_buf", "host_checksum": host_checksum},
+        "gpu_launches": acq["launches"], "kernel": kernel, "kernel_ms": launch_ms,
+        "roofline": roofline_block(workload, kernel, launch_ms, rays_per_launch, alg_bytes, clk, on_chip=True),
+        "clocks": clk,
+    }
+    if cpu_seconds > 0:
+        line["cpu_baseline"] = cpu_acq_baseline(desc, p, cpu_seconds, extra_legs)
+    return line
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# light-transport workloads (BASELINE configs 4 and 5)
+# ----------------------------------------------------------------------------------------------------------------------
+def pt_scene(args, workload, spp_step=None):
     from prt_b200 import scenes
-    from prt_b200.distributed import shard_samples
     if workload.startswith("heightfield"):
         # BASELINE config 5: 9 999 392-triangle height field in a closed box, 3840x2160, 8 diffuse bounces, no RR
         n_side = int(workload.partition(":")[2] or 2237)
         width, height = (3840, 2160) if args.res == 2048 else (args.res, args.res * 9 // 16)
-        spp_step = args.spp if args.spp != C2_SPP else 2
+        spp_step = spp_step or (args.spp if args.spp != C2_SPP else 2)
         desc = scenes.heightfield_scene(n_side, (width, height), spp_step)
-        wl_label = (f"synthetic height field, {desc.n_triangles()} triangles in a closed box, {width}x{height}, all diffuse, "
-                    "8 bounces (max_depth 9), no RR")
+        label = (f"synthetic height field, {desc.n_triangles()} triangles in a closed box, {width}x{height}, all diffuse, "
+                 "8 bounces (max_depth 9), no RR")
     else:
         width = height = args.res
-        spp_step = args.spp if args.spp != C2_SPP else 16
+        spp_step = spp_step or (args.spp if args.spp != C2_SPP else 16)
         desc = scenes.cbox_scene(args.res, spp_step)
-        wl_label = f"scenes/cbox.xml at {width}x{height}, path integrator max_depth 6 rr_depth 5, tent filter"
+        label = f"scenes/cbox.xml at {width}x{height}, path integrator max_depth 6 rr_depth 5, tent filter"
+    return desc, label, width, height, spp_step
+
+
+def pt_measure(args, workload, steps, warmup, rank, world, device, e2e_steps, cpu_seconds):
+    """One step = one batch of `spp` samples per pixel per GPU accumulated into the film; the K timed steps are ONE job:
+    film zeroed once, K batches, then ONE all-reduce of the RGBW film (BASELINE config 4: a 4096-spp job is 256 such
+    batches and one all-reduce)."""
+    import torch
+    import torch.distributed as dist
+    from prt_b200 import mi_compat as mi
+    from prt_b200.distributed import shard_samples
+    desc, label, width, height, spp_step = pt_scene(args, workload)
     scene = mi.Scene(desc)
     integ = scene.integrator()
     dev = scene.device()
@@ -177,15 +380,11 @@ def pt_measure(args, workload, steps, warmup, rank, world, device, e2e_steps, cp
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    def step(seed):
-        film.zero_()
-        dev.render_path_dev(rp, film.data_ptr(), stats.data_ptr(), stream.cuda_stream, seed=seed, spp=spp_total,
-                            sample_offset=off, sample_stride=stride)
-        if world > 1:
-            dist.all_reduce(film, op=dist.ReduceOp.SUM)
-
     for w in range(warmup):
-        step(1000 + w)
+        dev.render_path_dev(rp, film.data_ptr(), stats.data_ptr(), stream.cuda_stream, seed=1000 + w, spp=spp_total,
+                            sample_offset=off, sample_stride=stride)
+    if world > 1:
+        dist.all_reduce(film, op=dist.ReduceOp.SUM)
     barrier()
     stats.zero_()
     clocks = ClockSampler(device.index)
@@ -194,25 +393,32 @@ def pt_measure(args, workload, steps, warmup, rank, world, device, e2e_steps, cp
     ev = []
     barrier()
     dev.ctx.profile_begin()                 # event pairs around every kernel group, on the launching stream
+    e_first = torch.cuda.Event(enable_timing=True)
+    e_first.record(stream)
+    film.zero_()
+    e_zero = torch.cuda.Event(enable_timing=True)
+    e_zero.record(stream)
     for k in range(steps):
-        flush.fill_(k & 0xff)
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        if k:
+            flush.fill_(k & 0xff)           # L2 flush between timed batches; its time is taken out below
         e[0].record(stream)
-        film.zero_()
-        e[1].record(stream)
         dev.render_path_dev(rp, film.data_ptr(), stats.data_ptr(), stream.cuda_stream, seed=k, spp=spp_total, sample_offset=off,
                             sample_stride=stride)
-        e[2].record(stream)
-        if world > 1:
-            dist.all_reduce(film, op=dist.ReduceOp.SUM)
-        e[3].record(stream)
+        e[1].record(stream)
         ev.append(e)
+    e_red = torch.cuda.Event(enable_timing=True)
+    e_red.record(stream)
+    if world > 1:
+        dist.all_reduce(film, op=dist.ReduceOp.SUM)
+    e_last = torch.cuda.Event(enable_timing=True)
+    e_last.record(stream)
     barrier()
     clk = clocks.stop()
     classes = dev.ctx.profile_read()
-    t_local = torch.tensor([sum(e[0].elapsed_time(e[3]) for e in ev)], dtype=torch.float64, device=device)
-    kern_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
-    st_local = stats.cpu().numpy()
+    job_ms = e_first.elapsed_time(e_zero) + sum(e[0].elapsed_time(e[1]) for e in ev) + e_red.elapsed_time(e_last)
+    t_local = torch.tensor([job_ms], dtype=torch.float64, device=device)
+    st_local = stats.cpu().numpy().copy()
     st_all = stats.clone()
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
@@ -221,10 +427,9 @@ def pt_measure(args, workload, steps, warmup, rank, world, device, e2e_steps, cp
     hs = st_all.cpu().numpy()
     paths, segments, rays, shadow = (int(x) for x in hs[:4])
     value = rays / (total_ms * 1e-3) / 1e6
-    # end to end: mi.render(scene) -> developed numpy image on the host (page-locked), every step
-    # warm-up: a caller holds the previous image while the next one renders, so the page-locked result pool needs two
-    # buffers before it reaches its steady state
-    keep = [integ.render(scene, seed=77, spp=spp_total), integ.render(scene, seed=78, spp=spp_total)]
+    del flush
+    # end to end: mi.render(scene) -> developed numpy image on the host (page-locked), every call a complete job
+    keep = [integ.render(scene, seed=77, spp=spp_total), integ.render(scene, seed=78, spp=spp_total)]   # result pool warm-up
     del keep
     barrier()
     e2e_rays = 0
@@ -239,109 +444,122 @@ def pt_measure(args, workload, steps, warmup, rank, world, device, e2e_steps, cp
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     if rank != 0:
         return None
-    peak, peak_src, _ = measured_peaks()
     n_tris = desc.n_triangles()
-    # dominant kernel: the closest-hit trace kernel (one launch per bounce and batch); this rank's own counts
-    tc = classes.get("trace_closest", {"ms": 0.0, "launches": 0})
-    closest_local = int(st_local[2]) - int(st_local[3])
-    per_ray = bvh_min_bytes(n_tris) + WF_RAY_RECORD_BYTES
-    if tc["launches"]:
-        dom, dom_ms = "prt::k_wf_trace<false>", tc["ms"] / tc["launches"]
-        alg_bytes = closest_local * per_ray / tc["launches"]
-    else:                                              # PRT_PT_MODE=mega
-        mk = classes.get("megakernel", {"ms": kern_ms * steps, "launches": steps})
-        dom, dom_ms = "prt::k_render_path", mk["ms"] / max(mk["launches"], 1)
-        alg_bytes = int(st_local[2]) * bvh_min_bytes(n_tris) / max(mk["launches"], 1) + film.numel() * 4
-    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    traffic, traffic_src = ncu_traffic(workload)
     n_launch = sum(c["launches"] for c in classes.values())
+    step_kernels = sum(c["ms"] for c in classes.values())
+    tc = classes.get("trace_closest", {"ms": 0.0, "launches": 0})
+    mk = classes.get("megakernel", {"ms": 0.0, "launches": 0})
+    if mk["launches"]:                                 # resident-scene kernel (scenes that fit shared memory) or PRT_PT_MODE=mega
+        dom = "prt::k_render_resident" if n_tris <= 64 and os.environ.get("PRT_PT_MODE", "r")[0] != "m" else "prt::k_render_path"
+        dom_ms = mk["ms"] / mk["launches"]
+        rays_launch = int(st_local[2]) / mk["launches"]
+        alg_bytes = film.numel() * 4 * 2               # the film tile read-modify-write is all that leaves the SM
+        share = mk["ms"] / max(step_kernels, 1e-9)
+    else:
+        dom, dom_ms = "prt::k_wf_trace<false>", tc["ms"] / max(tc["launches"], 1)
+        rays_launch = (int(st_local[2]) - int(st_local[3])) / max(tc["launches"], 1)
+        alg_bytes = rays_launch * (bvh_min_bytes(n_tris) + WF_RAY_RECORD_BYTES)
+        share = tc["ms"] / max(step_kernels, 1e-9)
     line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "msamples_per_s": paths / (total_ms * 1e-3) / 1e6,
-            "config": {"workload": wl_label,
-                       "spp_per_gpu_per_step": spp_step, "paths_per_gpu_per_step": width * height * n_s, "n_triangles": n_tris,
-                       "bvh": {"nodes": bvh["n_nodes"], "nodes8": bvh.get("n_nodes8"), "build_ms": bvh["build_ms"],
-                               "sah_cost": bvh["sah_cost"], "device_bytes": bvh["device_bytes"]},
-                       "n_analytic": desc.n_analytic(), "segments_per_path": segments / max(paths, 1),
-                       "rays_per_path": rays / max(paths, 1),
-                       "parallelism": f"sample-shards x{world}, BVH replicated, 1 NCCL all-reduce of {film.numel() * 4} B",
-                       "l2": "flushed between timed steps (384 MiB fill, untimed)"},
+            "config": {"workload": label, "spp_per_gpu_per_step": spp_step, "paths_per_gpu_per_step": width * height * n_s,
+                       "n_triangles": n_tris, "n_analytic": desc.n_analytic(),
+                       "parallelism": f"sample-shards x{world}, BVH replicated, ONE NCCL all-reduce of the {film.numel() * 4} B film per job",
+                       "l2": "flushed between timed batches (384 MiB fill, untimed)"},
+            "bvh": {"nodes": bvh["n_nodes"], "nodes8": bvh.get("n_nodes8"), "build_ms": bvh["build_ms"],
+                    "bvh8_build_ms": bvh.get("bvh8_build_ms"), "sah_cost": bvh["sah_cost"], "device_bytes": bvh["device_bytes"]},
+            "segments_per_path": segments / max(paths, 1), "rays_per_path": rays / max(paths, 1),
             "e2e": {"value": e2e_rays / float(t_e2e.item()) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 512,
                     "d2h_bytes_per_step": int(height * width * 3 * 4 + 64), "steps": e2e_steps,
                     "api": "mi.render(scene) -> developed numpy image [H,W,3]", "host_checksum": checksum},
-            "gpu_launches": n_launch, "kernel": dom, "kernel_ms": dom_ms, "step_kernels_ms": kern_ms,
-            "kernel_classes": {k: {"ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] / steps,
-                                   "share": v["ms"] / max(sum(c["ms"] for c in classes.values()), 1e-9)}
-                               for k, v in classes.items()},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": f"dominant kernel {dom}: closest-hit rays x ({bvh_min_bytes(n_tris)} B B_min(N) of node + triangle "
-                                 f"fetches, SURVEY 8(d), + {WF_RAY_RECORD_BYTES} B ray/hit records) / its CUDA-event time; "
-                                 + ("scene lives on chip" if n_tris < 100000 else "scene >> L2: fetches go to HBM")},
+            "gpu_launches": n_launch, "kernel": dom, "kernel_ms": dom_ms, "kernel_share_of_step": share,
+            "kernel_classes": {k: {"ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] / steps}
+                               for k, v in classes.items() if v["launches"]},
+            "roofline": roofline_block(workload, dom, dom_ms, rays_launch, alg_bytes, clk, on_chip=n_tris < 100000),
             "clocks": clk}
-    wipr = ncu_entry(workload).get("warp_inst_per_ray")
-    if wipr and clk.get("sm_mhz") and tc["launches"]:
-        ray_rate = closest_local / (tc["ms"] * 1e-3)          # closest-hit rays per second inside k_wf_trace<false>
-        peak_issue = 148 * 4 * clk["sm_mhz"] * 1e6
-        line["issue"] = {"warp_inst_per_ray": wipr, "achieved_ginst_s": ray_rate * wipr / 1e9, "peak_ginst_s": peak_issue / 1e9,
-                         "frac": ray_rate * wipr / peak_issue, "source": ncu_entry(workload).get("source")}
-    if cpu_baseline:
-        import orc_py
-        threads = os.cpu_count() or 1
-        cres, cspp = 256, 16                      # the cbox tutorial resolution, 16 spp: ~1 M paths
-        cdesc = scenes.cbox_scene(cres, cspp)
-        csc = mi.Scene(cdesc)
-        crp = csc.integrator().render_params(csc)
-        osc = orc_py.OracleScene(cdesc)
-        t0 = time.perf_counter()
-        _, cst = orc_py.render_path(osc, crp, seed=0, spp=cspp, prec=32, n_threads=threads)
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": cst["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                                "sample": f"{cres}x{cres} x {cspp} spp of the same scene, oracle f32, {threads} threads, {dt:.1f} s"}
+    if cpu_seconds > 0:
+        line["cpu_baseline"] = cpu_pt_baseline(args, workload)
     return line
 
 
-def run_pt(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    line = pt_measure(args, args.workload, args.steps, args.warmup, rank, world, device, args.e2e_steps or min(args.steps, 3),
-                      world == 1 and not args.no_cpu_baseline and not args.workload.startswith("heightfield"))
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+WF_RAY_RECORD_BYTES = 64 + 16      # ray record read (4 x float4) + hit record written, per closest-hit query
+
+
+def cpu_pt_baseline(args, workload):
+    import orc_py
+    from prt_b200 import scenes
+    import CustomIntegrator
+    import CustomSensor
+    threads = os.cpu_count() or 1
+    if workload.startswith("heightfield"):
+        n_side, res, spp = 708, (256, 144), 4      # the oracle's BVH build over 10 M triangles takes ~40 s: a 1.0 M-triangle
+        cdesc = scenes.heightfield_scene(n_side, res, spp)   # instance of the same surface bounds the rate from above
+        what = f"{cdesc.n_triangles()}-triangle instance of the same height field, {res[0]}x{res[1]} x {spp} spp"
+    else:
+        res, spp = (256, 256), 16                   # the cbox tutorial resolution, 16 spp: ~1 M paths
+        cdesc = scenes.cbox_scene(res[0], spp)
+        what = f"{res[0]}x{res[1]} x {spp} spp of the same scene"
+    integ = CustomIntegrator.PathIntegrator(cdesc.integrator)
+    sensor = CustomSensor.PerspectiveSensor(cdesc.sensor)
+    sensor._film, sensor._sampler, sensor._rfilter = cdesc.film, cdesc.sampler, cdesc.rfilter
+    crp = integ.render_params(type("S", (), {"sensors": lambda self: [sensor]})())
+    osc = orc_py.OracleScene(cdesc)
+    t0 = time.perf_counter()
+    _, cst = orc_py.render_path(osc, crp, seed=0, spp=spp, prec=32, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": cst["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+            "sample": f"{what}, oracle f32, {threads} threads, {dt:.1f} s"}
+
+
+def compact(line):
+    """An `also` entry: what the driver's 1 500-character tail has room for."""
+    r = lambda x, n=4: None if x is None else float(f"{x:.{n}g}")
+    rf = line["roofline"]
+    out = {"value": r(line["value"], 5), "msamples": r(line["msamples_per_s"], 5), "e2e": r(line["e2e"]["value"], 5),
+           "ms": r(line["ms_per_step"]), "n": line["n_gpus"], "ck": r(line["e2e"]["host_checksum"], 3),
+           "kernel": line["kernel"].replace("prt::", ""), "bound": rf["bound"], "frac": r(rf.get("frac"), 3),
+           "dram_frac": r(rf["hbm"].get("dram_frac"), 3)}
+    if "cpu_baseline" in line:
+        out["cpu"] = r(line["cpu_baseline"]["value"])
+        out["cpu_cores"] = line["cpu_baseline"]["cores"]
+    return out
 
 
 def run_reference(args, rank: int):
-    """--impl reference: the CPU restatement of the reference path, all host threads, bounded sample per step."""
+    """--impl reference: the CPU restatement of the reference path on all host threads, the SAME job per step as the GPU arm
+    (one GPU's share: the weak-scaling unit) and the same `config`."""
     if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    if is_pt(args.workload):
+        t0 = time.perf_counter()
+        cb = cpu_pt_baseline(args, args.workload)
+        line = {"impl": "reference", "metric": "Mrays/s", "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": 1,
+                "warmup": 0, "ms_per_step": 1e3 * (time.perf_counter() - t0), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
         return
     from prt_b200.scene import AcqParams
     desc, label = workload_desc(args.workload)
     p = AcqParams.from_props(desc.integrator, desc.sensor)
-    threads = os.cpu_count() or 1
-    spp = C1_SPP
+    spp = args.spp
     for _ in range(args.warmup):
-        cpu_oracle_rate(desc, p, max(spp // 8, 1), 0, threads)
+        cpu_oracle_rate(desc, p, max(spp // 64, 1), 0, threads)      # short: page in the library, spin up the thread pool
     rays = paths = 0
     total = 0.0
     for k in range(args.steps):
         st, dt = cpu_oracle_rate(desc, p, spp, k, threads)
         rays += st["rays"]; paths += st["paths"]; total += dt
     val = rays / total / 1e6
-    sample = f"{spp * p.n_angles * p.n_elements} paths/step (BASELINE config 1 path count) of {label}"
+    sample = (f"{spp * p.n_angles * p.n_elements} paths/step = the GPU arm's per-GPU job, oracle f32 (C restatement of "
+              f"CustomIntegrator.simulate_acquisition_parallel), {threads} threads")
     line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "msamples_per_s": paths / total / 1e6,
-            "config": {"workload": label, "paths_per_step": spp * p.n_angles * p.n_elements, "max_depth": p.max_depth,
-                       "note": "CPU restatement (oracle port) of CustomIntegrator.simulate_acquisition_parallel; "
-                               "the unmodified reference needs mitsuba/drjit, not installable here"},
+            "config": acq_config(label, p, spp, args.gpus, desc.n_triangles(), desc.n_analytic()),
             "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -350,14 +568,16 @@ def run_reference(args, rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sphere_box")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--spp", type=int, default=C2_SPP, help="samples per (angle, element) per GPU and step")
     ap.add_argument("--res", type=int, default=2048, help="film resolution of the cbox workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="skip the short cbox measurement appended to the default line")
+    ap.add_argument("--also", default=None, help=f"comma list of workloads measured briefly in the same job (default for the "
+                                                 f"headline workload: {DEFAULT_ALSO}; 'none' to skip)")
+    ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: min(steps, 5))")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -367,216 +587,47 @@ def main():
         run_reference(args, rank)
         return
     args.warmup = max(args.warmup, 3)
-    if args.workload == "cbox" or args.workload.startswith("heightfield"):
-        run_pt(args, rank, world, local_rank)
-        return
 
     import torch
     import torch.distributed as dist
-    from prt_b200 import mi_compat as mi
-    from prt_b200.distributed import shard_samples
-    from prt_b200.scene import AcqParams
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-
-    desc, label = workload_desc(args.workload)
-    scene = mi.Scene(desc)
-    integ = scene.integrator()
-    dev = scene.device()
-    p = integ.acq_params(scene)
-    n_ae = p.n_angles * p.n_elements
-    spp_total = args.spp * world                       # weak scaling: per-GPU work fixed
-    off, stride, n_s = shard_samples(spp_total, rank, world)
-
-    buf = torch.zeros((p.n_angles, p.n_elements, p.time_samples), dtype=torch.float32, device=device)
-    tx = torch.zeros((p.n_angles, p.n_elements), dtype=torch.float32, device=device)
-    stats = torch.zeros(8, dtype=torch.int64, device=device)
-    flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=device)   # > 126 MB L2
-    stream = torch.cuda.current_stream(device)
-
-    from prt_b200.distributed import acquire_allreduce_pipelined
-
-    def step(seed: int):
-        buf.zero_()
-        # one launch per steering angle; with N > 1 the all-reduce of angle a's slice overlaps the kernel of angle a + 1
-        acquire_allreduce_pipelined(dev, p, buf, tx, stats, stream, seed, spp_total, off, stride, dist, world)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(device)
-
-    for w in range(args.warmup):
-        step(1000 + w)
-    barrier()
-    stats.zero_()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    time.sleep(0.4)                                 # let nvidia-smi start sampling before the timed region
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    barrier()
-    dev.ctx.profile_begin()                         # event pair around every k_acquire launch, on the launching stream
-    wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.fill_(k & 0xff)                       # L2 flush between timed iterations (untimed)
-        e0, e1, e2 = ev[k]
-        e0.record(stream)
-        buf.zero_()
-        e1.record(stream)
-        acquire_allreduce_pipelined(dev, p, buf, tx, stats, stream, k, spp_total, off, stride, dist, world)
-        e2.record(stream)
-        ev[k] = (e0, e1, e2, torch.cuda.Event(enable_timing=True))
-        ev[k][3].record(stream)
-    barrier()
-    wall = time.perf_counter() - wall0
-    clk = clocks.stop()
-    classes = dev.ctx.profile_read()
-    step_ms = [e[0].elapsed_time(e[3]) for e in ev]
-    kern_ms = [e[1].elapsed_time(e[2]) for e in ev]
-    t_local = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
-    st_all = stats.clone()
-    if world > 1:
-        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
-        dist.all_reduce(st_all, op=dist.ReduceOp.SUM)
-    total_ms = float(t_local.item())
-    hs = st_all.cpu().numpy()
-    paths, segments, rays, deposits = int(hs[0]), int(hs[1]), int(hs[2]), int(hs[3])
-    value = rays / (total_ms * 1e-3) / 1e6
-
-    # ---- end to end through the reference-facing plugin call, HOST results -----------------------------------
-    integ.samples_per_element = spp_total
+    cpu_s = 0.0 if (world > 1 or args.no_cpu_baseline) else 10.0
     e2e_steps = args.e2e_steps or min(args.steps, 5)
-    integ.seed = 999
-    _quiet = open(os.devnull, "w")
-    so = sys.stdout
-    sys.stdout = _quiet                              # the reference's method prints; keep ONE JSON line on stdout
-    try:
-        integ.simulate_acquisition_parallel(scene)  # warm-up (allocates the pinned result buffers: the pool needs
-        integ.simulate_acquisition_parallel(scene)  # two, because the integrator still holds the previous result)
-        barrier()
-        e2e_rays = 0
-        t0 = time.perf_counter()
-        for k in range(e2e_steps):
-            integ.seed = 2000 + k
-            integ.simulate_acquisition_parallel(scene)
-            e2e_rays += int(integ.last_stats["rays"])
-            host_checksum = float(integ.channel_buf.ravel()[::997].sum())   # touch the HOST result (strided: a full
-            #                                                                  sum of 12.8 MB costs more than the kernel)
-        barrier()
-        e2e_dt = time.perf_counter() - t0
-    finally:
-        sys.stdout = so
-    t_e2e = torch.tensor([e2e_dt], dtype=torch.float64, device=device)
-    r_e2e = torch.tensor([e2e_rays], dtype=torch.int64, device=device)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        # acquire_sharded already all-reduces the stats, so every rank holds the global ray count
-    e2e_value = float(r_e2e.item()) / float(t_e2e.item()) / 1e6
-    d2h = buf.numel() * 4 + tx.numel() * 4 + 64
-    h2d = 8 * p.n_angles + 512                       # angle table + kernel parameter block
-
-    if rank == 0:
-        peak, peak_src, sm_max = measured_peaks()
-        n_tris = desc.n_triangles()
-        k_ms = float(np.mean(kern_ms))             # all k_acquire launches of one step (one per steering angle)
-        acq = classes.get("acquire", {"ms": k_ms * args.steps, "launches": args.steps})
-        launch_ms = acq["ms"] / max(acq["launches"], 1)
-        rays_per_launch = rays / world / max(acq["launches"], 1)
-        # algorithmic bytes per launch: BVH descent per ray (0 for analytic scenes, which live
-        # in shared memory) + this launch's slice of the channel buffer written once (the megakernel streams no
-        # per-segment state)
-        alg_bytes = rays_per_launch * bvh_min_bytes(n_tris) + buf.numel() * 4 * args.steps / max(acq["launches"], 1)
-        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic(args.workload)
-        line = {
-            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "msamples_per_s": paths / (total_ms * 1e-3) / 1e6, "msegments_per_s": segments / (total_ms * 1e-3) / 1e6,
-            "config": {"workload": label, "paths_per_gpu_per_step": int(n_ae * n_s), "spp_per_gpu": args.spp,
-                       "n_angles": p.n_angles, "n_elements": p.n_elements, "time_samples": p.time_samples,
-                       "max_depth": p.max_depth, "n_triangles": n_tris, "n_analytic": desc.n_analytic(),
-                       "parallelism": f"sample-shards x{world}, BVH replicated, NCCL sum all-reduce of {buf.numel() * 4} B "
-                                      f"issued per steering-angle slice so that it overlaps the next angle's kernel",
-                       "l2": "flushed between timed steps (384 MiB fill, untimed); inputs are < 10 KB and live on chip by design",
-                       "segments_per_path": segments / max(paths, 1), "rays_per_path": rays / max(paths, 1)},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "api": "UltraIntegrator.simulate_acquisition_parallel(scene) -> numpy channel_buf",
-                    "host_checksum": host_checksum},
-            "gpu_launches": acq["launches"], "kernel": "prt::k_acquire<%s>" % ("true" if n_tris else "false"),
-            "kernel_ms": launch_ms, "step_kernels_ms": k_ms,
-            "wall_s_timed_region": wall,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": ("mesh scene: rays x B_min(N) = %d B of node + triangle fetches (SURVEY 8(d)); the tree lives on "
-                                  "chip, the kernel is bound by traversal latency / SIMT divergence" % bvh_min_bytes(n_tris)) if n_tris else
-                                 ("analytic scenes stage <= 8 KB of primitives in shared memory and the 12.8 MB accumulator "
-                                  "stays in L2: this configuration is instruction-issue bound, not HBM bound (see `issue`)")},
-            "clocks": clk,
-        }
-        # instruction-issue view (the binding limit when the scene lives on chip): warp instructions per ray from the
-        # committed ncu capture (profiles/traffic.json) x this run's rays/s, against 4 schedulers x 148 SMs x the SM
-        # clock sampled during the timed region
-        wipr = ncu_entry(args.workload).get("warp_inst_per_ray")
-        if wipr and clk.get("sm_mhz"):
-            ray_rate = rays_per_launch / (launch_ms * 1e-3)
-            peak_issue = 148 * 4 * clk["sm_mhz"] * 1e6
-            line["issue"] = {"warp_inst_per_ray": wipr, "achieved_ginst_s": ray_rate * wipr / 1e9,
-                             "peak_ginst_s": peak_issue / 1e9, "frac": ray_rate * wipr / peak_issue,
-                             "source": ncu_entry(args.workload).get("source")}
-        if n_tris == 0 and clk.get("sm_mhz"):
-            # fp32 view of SURVEY 8(d): ~740 flop per segment (2 queries x 255 + UltraBSDF 150 + glue 80) on analytic scenes
-            seg_rate = (segments / world / max(acq["launches"], 1)) / (launch_ms * 1e-3)
-            peak_tf = 148 * 128 * 2 * clk["sm_mhz"] * 1e6 / 1e12
-            line["fp32"] = {"flop_per_segment": 740, "achieved_tflops": seg_rate * 740 / 1e12, "peak_tflops": peak_tf,
-                            "frac": seg_rate * 740 / 1e12 / peak_tf, "note": "SURVEY 8(d) estimate; sqrt/exp/sin/acos counted as 1"}
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            st, dt = cpu_oracle_rate(desc, p, C1_SPP, 0, threads)
-            reps = int(min(max(10.0 / max(dt, 1e-3), 1), 2000))   # ~10 s of CPU work, bounded
-            rays_c, t_c = st["rays"], dt
-            for k in range(1, reps):
-                st, dt = cpu_oracle_rate(desc, p, C1_SPP, k, threads)
-                rays_c += st["rays"]; t_c += dt
-            line["cpu_baseline"] = {"value": rays_c / t_c / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                                    "sample": f"{reps} x {C1_SPP * n_ae} paths (BASELINE config 1 path count) of the same scene, "
-                                              f"oracle f32, {threads} threads, {t_c:.1f} s"}
-            # SURVEY 8(d) also asks for (ii) the restatement on ONE thread and (iii) a pure-Python transliteration of
-            # _trace_single_ray on the literal 320-path acquisition, as a proxy for the reference's interpreter-bound loop
-            st1, dt1 = cpu_oracle_rate(desc, p, C1_SPP, 0, 1)
-            line["cpu_baseline"]["single_thread"] = {"value": st1["rays"] / dt1 / 1e6, "unit": "Mrays/s", "cores": 1,
-                                                     "sample": f"{C1_SPP * n_ae} paths, oracle f32, {dt1:.1f} s"}
-            try:
-                import pyref
-                shapes_py = pyref.shapes_from_desc(desc)
-                t0 = time.perf_counter()
-                _, _, stp = pyref.acquire(shapes_py, p, seed=0, spp=1)
-                dtp = time.perf_counter() - t0
-                line["cpu_baseline"]["pure_python"] = {"value": stp["rays"] / dtp / 1e6, "unit": "Mrays/s", "cores": 1,
-                                                       "sample": f"{n_ae} paths (the reference's literal acquisition: 1 path per "
-                                                                 f"(angle, element)), oracle/pyref.py, {dtp:.2f} s"}
-            except ValueError:
-                pass                         # pyref handles sphere / rectangle scenes only
+    if is_pt(args.workload):
+        line = pt_measure(args, args.workload, args.steps, args.warmup, rank, world, device, min(e2e_steps, 3), cpu_s)
     else:
-        line = None
-    if not args.no_also:
-        # the other scene BASELINE.json's metric names (scenes/cbox.xml, config 4), measured briefly in the same job:
-        # wavefront path tracer, sample shards + one all-reduce of the film
-        del buf, flush
+        line = acq_measure(args, args.workload, args.steps, args.warmup, rank, world, device, e2e_steps, cpu_s, extra_legs=True)
+    if rank == 0 and not is_pt(args.workload):
+        # a headline that computes nothing is not a measurement (round-1 lesson): the default workload must deposit energy
+        if args.workload == DEFAULT_WORKLOAD:
+            assert line["deposits_per_path"] > 0 and line["device_checksum"] > 0 and line["e2e"]["host_checksum"] > 0, \
+                "headline workload deposited nothing"
+    also = args.also if args.also is not None else (DEFAULT_ALSO if args.workload == DEFAULT_WORKLOAD else "none")
+    entries = {}
+    if not args.no_also and also != "none":
         torch.cuda.empty_cache()
-        cb = pt_measure(args, "cbox", 3, 3, rank, world, device, 2, False)
-        if rank == 0:
-            line["also"] = {"cbox": {k: cb[k] for k in ("value", "unit", "ms_per_step", "msamples_per_s", "e2e", "gpu_launches",
-                                                         "kernel", "kernel_ms", "kernel_classes", "roofline", "issue", "config")
-                                     if k in cb}}
+        cpu_a = 0.0 if cpu_s == 0 else 3.0
+        for wl in [w for w in also.split(",") if w and w != args.workload]:
+            try:
+                if is_pt(wl):
+                    sub = pt_measure(args, wl, 3, 3, rank, world, device, 2, cpu_a)
+                else:
+                    sub = acq_measure(args, wl, 5, 3, rank, world, device, 2, cpu_a)
+                if rank == 0:
+                    entries[wl] = compact(sub)
+            except Exception as ex:      # an `also` failure must not take the headline line down with it
+                if rank == 0:
+                    entries[wl] = {"error": f"{type(ex).__name__}: {ex}"[:160]}
+            torch.cuda.empty_cache()
     if rank == 0:
+        line.pop("kernel_classes", None) if entries else None
+        if entries:
+            line["also"] = entries              # LAST key: survives the driver's stdout tail
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -95,7 +95,8 @@ typedef struct {
     uint32_t n_nodes8;          /* nodes of the compressed 8-wide BVH (80 B each), 0 = none */
     uint32_t bvh8_levels;
     float    bvh8_build_ms;     /* collapse + quantisation + triangle reorder, CUDA-event timed */
-    float    _pad;
+    uint32_t n_oversized;       /* triangles kept out of the hierarchy and tested one by one (bounding-box area > 1024 x the
+                                   scene's mean, at most 64): n_nodes == n_triangles - n_oversized - 1 */
 } prt_bvh_stats;
 /* SoA upload + GPU LBVH build (Morton codes -> radix sort -> Karras hierarchy -> bottom-up refit) */
 int prt_scene_commit(prt_scene *, prt_bvh_stats *out /* nullable */);

@@ -60,13 +60,14 @@ class BvhStatsC(C.Structure):
     _fields_ = [("n_primitives", C.c_uint32), ("n_triangles", C.c_uint32), ("n_nodes", C.c_uint32),
                 ("max_leaf_size", C.c_uint32), ("build_ms", C.c_float), ("sah_cost", C.c_float),
                 ("scene_lo", C.c_float * 3), ("scene_hi", C.c_float * 3), ("device_bytes", C.c_uint64),
-                ("n_nodes8", C.c_uint32), ("bvh8_levels", C.c_uint32), ("bvh8_build_ms", C.c_float), ("_pad", C.c_float)]
+                ("n_nodes8", C.c_uint32), ("bvh8_levels", C.c_uint32), ("bvh8_build_ms", C.c_float), ("n_oversized", C.c_uint32)]
 
     def as_dict(self):
         return dict(n_primitives=self.n_primitives, n_triangles=self.n_triangles, n_nodes=self.n_nodes,
                     max_leaf_size=self.max_leaf_size, build_ms=self.build_ms, sah_cost=self.sah_cost,
                     scene_lo=list(self.scene_lo), scene_hi=list(self.scene_hi), device_bytes=self.device_bytes,
-                    n_nodes8=self.n_nodes8, bvh8_levels=self.bvh8_levels, bvh8_build_ms=self.bvh8_build_ms)
+                    n_nodes8=self.n_nodes8, bvh8_levels=self.bvh8_levels, bvh8_build_ms=self.bvh8_build_ms,
+                    n_oversized=self.n_oversized)
 
 
 KERNEL_CLASSES = ("generate", "trace_closest", "trace_shadow", "shade", "film", "acquire", "megakernel", "other")

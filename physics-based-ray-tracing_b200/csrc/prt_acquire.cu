@@ -649,12 +649,14 @@ int prt_acquire_trace(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint
     uint64_t *idx_d = nullptr;
     prt_seg_record *rec_d = nullptr;
     const size_t nrec = (size_t) n * (size_t) (p->max_depth > 0 ? p->max_depth : 1);
-    PRT_CUDA(cudaMalloc(&idx_d, sizeof(uint64_t) * n));
-    PRT_CUDA(cudaMalloc(&rec_d, sizeof(prt_seg_record) * nrec));
-    PRT_CUDA(cudaMemcpyAsync(idx_d, path_idx, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
-    PRT_CUDA(cudaMemsetAsync(rec_d, 0, sizeof(prt_seg_record) * nrec, st));
-    k_acquire_trace<<<(unsigned) ((n + ACQ_THREADS - 1) / ACQ_THREADS), ACQ_THREADS, 0, st>>>(P, idx_d, n, rec_d);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaMalloc(&idx_d, sizeof(uint64_t) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&rec_d, sizeof(prt_seg_record) * nrec);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(idx_d, path_idx, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(rec_d, 0, sizeof(prt_seg_record) * nrec, st);
+    if (e == cudaSuccess) {
+        k_acquire_trace<<<(unsigned) ((n + ACQ_THREADS - 1) / ACQ_THREADS), ACQ_THREADS, 0, st>>>(P, idx_d, n, rec_d);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(rec, rec_d, sizeof(prt_seg_record) * (size_t) n * (size_t) p->max_depth, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(idx_d);

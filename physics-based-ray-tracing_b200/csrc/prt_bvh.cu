@@ -5,6 +5,8 @@
 // Replaces the Embree BVH build hidden inside mi.load_dict (/root/reference/USMain.py:257).
 // Node layout: prt_device.cuh (64 B, both child boxes inline).
 #include <cfloat>
+#include <string>
+#include <vector>
 
 #include "prt_internal.h"
 
@@ -73,10 +75,14 @@ __global__ void k_morton(const float4 *__restrict__ tv, uint32_t n, const unsign
     }
     float4 a = tv[3 * (size_t) i], b = tv[3 * (size_t) i + 1], c = tv[3 * (size_t) i + 2];
     float cc[3] = { (a.x + b.x + c.x) * (1.0f / 3.0f), (a.y + b.y + c.y) * (1.0f / 3.0f), (a.z + b.z + c.z) * (1.0f / 3.0f) };
+    // ONE scale for the three axes (cubic cells).  Normalising every axis by its own extent turns a thin slab of geometry --
+    // a height field: 2 x 2 x 0.14 -- into a cube, so a third of the Morton bits split it by HEIGHT into layers that overlap
+    // completely in the other two directions (measured: SAH cost 220 instead of 54 on the 10 M-triangle floor).
+    const float emax = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
     uint64_t q[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        float u = ext[k] > 0.0f ? (cc[k] - lo[k]) / ext[k] : 0.0f;
+        float u = emax > 0.0f ? (cc[k] - lo[k]) / emax : 0.0f;
         u = fminf(fmaxf(u, 0.0f), 1.0f);
         q[k] = (uint64_t) fminf(u * 2097152.0f, 2097151.0f);
     }
@@ -214,6 +220,8 @@ static int exclusive_scan(uint32_t *data, uint32_t n, uint32_t *scratch, cudaStr
     k_scan_add<<<nb, SC_THREADS, 0, st>>>(data, n, scratch);
     return 0;
 }
+
+int exclusive_scan_u32(uint32_t *data, uint32_t n, uint32_t *scratch, cudaStream_t st) { return exclusive_scan(data, n, scratch, st); }
 
 // ---- Karras 2012 ----------------------------------------------------------------------------------
 __device__ __forceinline__ int delta(const uint64_t *__restrict__ keys, int n, int i, int j) {
@@ -368,6 +376,40 @@ __global__ void k_sah(int n, const float *__restrict__ nodes, const int2 *__rest
     (void) parent_internal;
 }
 
+// depth of the binary tree = the longest leaf-to-root parent chain (the traversal stack must hold one entry per level)
+__global__ void k_depth(int n, const int *__restrict__ parent_internal, const int *__restrict__ parent_leaf, int *max_depth) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int d = 0;
+    if (i < n)
+        for (int p = parent_leaf[i]; p >= 0; p = parent_internal[p]) d++;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0 && d) atomicMax(max_depth, d);
+}
+
+namespace {
+// every temporary of the build: released on EVERY exit path (the PRT_CUDA macro returns on the first error)
+struct BuildTemps {
+    std::vector<void *> ptrs;
+    std::vector<cudaEvent_t> events;
+    ~BuildTemps() {
+        for (void *p : ptrs) cudaFree(p);
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+    }
+    template <typename T> cudaError_t alloc(T **out, size_t count) {
+        *out = nullptr;
+        cudaError_t e = cudaMalloc((void **) out, sizeof(T) * (count ? count : 1));
+        if (e == cudaSuccess) ptrs.push_back(*out);
+        return e;
+    }
+    cudaError_t event(cudaEvent_t *e) {
+        cudaError_t rc = cudaEventCreate(e);
+        if (rc == cudaSuccess) events.push_back(*e);
+        return rc;
+    }
+};
+}  // namespace
+
 int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri_v_out, uint32_t *order_out,
                float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t st, Bvh8Out *bvh8) {
     (void) ctx;
@@ -376,30 +418,32 @@ int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri
         *root_ref = -1;
         return PRT_OK;
     }
+    BuildTemps tmp;
     cudaEvent_t e0, e1;
-    PRT_CUDA(cudaEventCreate(&e0));
-    PRT_CUDA(cudaEventCreate(&e1));
+    PRT_CUDA(tmp.event(&e0));
+    PRT_CUDA(tmp.event(&e1));
     const uint32_t nb_sort = (n + RS_TILE - 1) / RS_TILE;
     const uint32_t hist_len = 256 * nb_sort;
     uint64_t *keys[2];
     uint32_t *vals[2], *hist, *scan_scratch;
     unsigned *bounds;
     int2 *children, *ranges;
-    int *parent_internal, *parent_leaf, *visit;
+    int *parent_internal, *parent_leaf, *visit, *depth_dev;
     float *root_box, *sah;
-    PRT_CUDA(cudaMalloc(&keys[0], sizeof(uint64_t) * n));
-    PRT_CUDA(cudaMalloc(&keys[1], sizeof(uint64_t) * n));
-    PRT_CUDA(cudaMalloc(&vals[0], sizeof(uint32_t) * n));
-    PRT_CUDA(cudaMalloc(&vals[1], sizeof(uint32_t) * n));
-    PRT_CUDA(cudaMalloc(&hist, sizeof(uint32_t) * hist_len));
-    PRT_CUDA(cudaMalloc(&scan_scratch, sizeof(uint32_t) * (hist_len / SC_TILE + 4096)));
-    PRT_CUDA(cudaMalloc(&bounds, sizeof(unsigned) * 8));
-    PRT_CUDA(cudaMalloc(&children, sizeof(int2) * n));
-    PRT_CUDA(cudaMalloc(&ranges, sizeof(int2) * n));
-    PRT_CUDA(cudaMalloc(&parent_internal, sizeof(int) * n));
-    PRT_CUDA(cudaMalloc(&parent_leaf, sizeof(int) * n));
-    PRT_CUDA(cudaMalloc(&visit, sizeof(int) * n));
-    PRT_CUDA(cudaMalloc(&root_box, sizeof(float) * 8));
+    PRT_CUDA(tmp.alloc(&keys[0], n));
+    PRT_CUDA(tmp.alloc(&keys[1], n));
+    PRT_CUDA(tmp.alloc(&vals[0], n));
+    PRT_CUDA(tmp.alloc(&vals[1], n));
+    PRT_CUDA(tmp.alloc(&hist, hist_len));
+    PRT_CUDA(tmp.alloc(&scan_scratch, hist_len / SC_TILE + 4096));
+    PRT_CUDA(tmp.alloc(&bounds, 8));
+    PRT_CUDA(tmp.alloc(&children, n));
+    PRT_CUDA(tmp.alloc(&ranges, n));
+    PRT_CUDA(tmp.alloc(&parent_internal, n));
+    PRT_CUDA(tmp.alloc(&parent_leaf, n));
+    PRT_CUDA(tmp.alloc(&visit, n));
+    PRT_CUDA(tmp.alloc(&root_box, 8));
+    PRT_CUDA(tmp.alloc(&depth_dev, 1));
     sah = root_box + 6;
     PRT_CUDA(cudaEventRecord(e0, st));
     const int T = 256;
@@ -424,14 +468,28 @@ int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri
         k_refit<<<nb, T, 0, st>>>(tri_v_out, (int) n, children, parent_internal, parent_leaf, (float *) nodes_out, visit, root_box);
         k_emit<<<nb, T, 0, st>>>((int) n, children, ranges, (float *) nodes_out);
         k_sah<<<nb, T, 0, st>>>((int) n, (const float *) nodes_out, ranges, parent_internal, root_box, sah);
+        PRT_CUDA(cudaMemsetAsync(depth_dev, 0, sizeof(int), st));
+        k_depth<<<nb, T, 0, st>>>((int) n, parent_internal, parent_leaf, depth_dev);
     }
     PRT_CUDA(cudaEventRecord(e1, st));
     PRT_CUDA(cudaStreamSynchronize(st));
     PRT_CUDA(cudaGetLastError());
+    if (n >= 2) {
+        // The binary traversal (traverse_bvh) pushes at most one entry per level and silently drops entries beyond PRT_STACK:
+        // a deeper tree would lose hits without any error.  63-bit Morton codes + index tie-break bound the depth by
+        // 63 + log2(duplicates), which only pathological inputs (tens of thousands of coincident centroids) approach.
+        int depth = 0;
+        PRT_CUDA(cudaMemcpy(&depth, depth_dev, sizeof(int), cudaMemcpyDeviceToHost));
+        if (depth > PRT_STACK) {
+            set_error("prt_scene_commit: the LBVH is " + std::to_string(depth) + " levels deep; the traversal stack holds " +
+                      std::to_string(PRT_STACK) + " (coincident triangles?)");
+            return PRT_ERR_UNSUPPORTED;
+        }
+    }
     if (bvh8) {
         cudaEvent_t b0, b1;
-        PRT_CUDA(cudaEventCreate(&b0));
-        PRT_CUDA(cudaEventCreate(&b1));
+        PRT_CUDA(tmp.event(&b0));
+        PRT_CUDA(tmp.event(&b1));
         PRT_CUDA(cudaEventRecord(b0, st));
         int rc = build_bvh8(n, tri_v_out, (const float *) nodes_out, children, ranges, &bvh8->nodes8, &bvh8->n_nodes8, &bvh8->tri_v8,
                             &bvh8->tri8_sorted, &bvh8->levels, st);
@@ -439,8 +497,6 @@ int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri
         PRT_CUDA(cudaEventRecord(b1, st));
         PRT_CUDA(cudaStreamSynchronize(st));
         PRT_CUDA(cudaEventElapsedTime(&bvh8->build_ms, b0, b1));
-        cudaEventDestroy(b0);
-        cudaEventDestroy(b1);
     }
     *root_ref = (n <= (uint32_t) MAX_LEAF) ? ~(int) ((0u << 2) | (n - 1)) : 0;
     if (stats) {
@@ -456,11 +512,7 @@ int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri
         stats->n_nodes = n >= 2 ? n - 1 : 0;
         stats->max_leaf_size = MAX_LEAF;
     }
-    cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(hist); cudaFree(scan_scratch);
-    cudaFree(bounds); cudaFree(children); cudaFree(ranges); cudaFree(parent_internal); cudaFree(parent_leaf);
-    cudaFree(visit); cudaFree(root_box);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    return PRT_OK;
+    return PRT_OK;      // ~BuildTemps releases every temporary
 }
 
 }  // namespace prt

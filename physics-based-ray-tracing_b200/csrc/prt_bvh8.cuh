@@ -54,10 +54,13 @@ __device__ __forceinline__ float byte_f(uint32_t w, int j) { return (float) ((w 
 
 // tests the (up to) eight children of node `idx`; returns the hit mask: bits 24..31 = inner children at position
 // 24 + (slot ^ octinv), bits 0..23 = triangles (offsets from tri_base); writes child_base / tri_base / imask
+// PLAIN: `nodes` is not global memory (a shared-memory copy of the top levels): ordinary loads instead of ld.global.nc
+template <bool PLAIN = false>
 __device__ __forceinline__ uint32_t bvh8_node(const float4 *__restrict__ nodes, uint32_t idx, const Bvh8Ray &r, float tmax,
                                               uint32_t &child_base, uint32_t &tri_base, uint32_t &imask) {
     const float4 *n = nodes + 5 * (size_t) idx;
-    const float4 n0 = ldg4(n), n1 = ldg4(n + 1), n2 = ldg4(n + 2), n3 = ldg4(n + 3), n4 = ldg4(n + 4);
+    const float4 n0 = PLAIN ? n[0] : ldg4(n), n1 = PLAIN ? n[1] : ldg4(n + 1), n2 = PLAIN ? n[2] : ldg4(n + 2),
+                 n3 = PLAIN ? n[3] : ldg4(n + 3), n4 = PLAIN ? n[4] : ldg4(n + 4);
     const uint32_t e = __float_as_uint(n0.w);
     imask = e >> 24;
     child_base = __float_as_uint(n1.x);

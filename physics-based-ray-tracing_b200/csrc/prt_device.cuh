@@ -46,6 +46,13 @@ struct DScene {
     const float4    *tri_n;    // [n_tris][3] world-space corner normals, sorted order (valid iff info.w & 1)
     const int4      *tri_info; // sorted order: {orig_index, shape, material, flags (1 = has normals, 2 = flip)}
     int n_prims, n_mats, n_tris, root_ref;
+    // Triangles [0, n_small) (sorted order) are in the hierarchy.  [n_small, n_tris) are OVERSIZED triangles (bounding-box
+    // area > 1024 x the scene's mean: the ten wall triangles of a closed box around ten million small ones) kept out of it
+    // and tested one by one before every traversal: in a Morton-ordered tree such a triangle inflates the box of every
+    // ancestor on its path to the full wall, and every ray near that wall then walks the whole chain.  (Embree handles the
+    // same case with spatial splits; a handful of brute-force tests is the GPU-cheap equivalent.)  v1.w of such a triangle
+    // = bits((sorted index << 2) | shading queue), like the BVH8 copies.
+    int n_small;
     // area emitters (light transport only): every emissive mesh shape is one emitter
     const float4    *em_tri;         // [n_em_tris][3]: v0 + running area (w), v1 + bits(material) (w), v2 + flip (w)
     const int       *em_first;       // [n_emitters + 1] ranges into em_tri
@@ -423,6 +430,25 @@ __device__ __forceinline__ float box_entry(float lox, float loy, float loz, floa
 
 #define PRT_STACK 48
 
+// the oversized triangles of the scene (DScene::n_small), nearest (or any) within [0, tbest]; returns the sorted index or -1
+template <bool ANY, typename RAYT>
+__device__ __forceinline__ int test_big_tris(const DScene &sc, const RAYT &rt, float3 o, float &tbest, float &b1, float &b2) {
+    int best = -1;
+    for (int j = sc.n_small; j < sc.n_tris; j++) {
+        const float4 *tv = sc.tri_v + 3 * (size_t) j;
+        const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
+#if PRT_TRI_ROWS
+        if (intersect_tri_rows(rt, o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#else
+        if (intersect_tri_wt(rt, o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#endif
+            best = j;
+            if (ANY) return best;
+        }
+    }
+    return best;
+}
+
 // nearest triangle (ANY = false) or any triangle (ANY = true) along the ray within [0, tbest].
 // returns the SORTED triangle index or -1; tbest/b1/b2 updated on a hit.
 template <bool ANY>
@@ -436,6 +462,14 @@ __device__ __forceinline__ int traverse_bvh(const DScene &sc, float3 o, float3 d
     int   stack_ref[PRT_STACK];
     float stack_t[PRT_STACK];
     int sp = 0, best = -1;
+    if (sc.n_small < sc.n_tris) {
+#if PRT_TRI_ROWS
+        best = test_big_tris<ANY>(sc, ray_rows(rp), o, tbest, b1, b2);
+#else
+        best = test_big_tris<ANY>(sc, rp, o, tbest, b1, b2);
+#endif
+        if ((ANY && best >= 0) || sc.n_small == 0) return best;
+    }
     int ref = sc.root_ref;
     const int DONE = 0x7fffffff;
     // pop the next entry whose box still starts before the current best hit

@@ -125,6 +125,7 @@ struct prt_scene {
     float  *em_inv_area_dev;
     int     n_emitters;
     uint32_t n_tris, n_nodes;
+    uint32_t n_small = 0;          // triangles in the hierarchy; the n_tris - n_small oversized ones sit behind them (DScene::n_small)
     int root_ref;
     uint64_t device_bytes;
     prt_bvh_stats stats;
@@ -150,6 +151,8 @@ int bvh8_annotate(uint32_t n, const uint32_t *tri8_sorted, const int4 *tri_info,
 int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, const int2 *children, const int2 *ranges,
                float4 **out_nodes8, uint32_t *out_n_nodes8, float4 **out_tri_v8, uint32_t **out_tri8_sorted, int *out_levels,
                cudaStream_t st);
+// exclusive prefix sum of n u32 in place; scratch: n / 2048 + 4096 words (prt_bvh.cu)
+int exclusive_scan_u32(uint32_t *data, uint32_t n, uint32_t *scratch, cudaStream_t st);
 int ensure_scratch(prt_context *ctx, size_t acc_floats, size_t aux_floats, size_t n_angles);
 int scratch_slot(prt_context *ctx, int slot, size_t bytes, void **out);
 int acquire_enqueue(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,

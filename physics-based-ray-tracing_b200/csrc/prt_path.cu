@@ -119,36 +119,36 @@ struct ResScene {
     int n_prims, n_tris;
 };
 
-__device__ __forceinline__ bool res_closest(const PtDev &P, const ResScene &R, float3 o, float3 d, Hit &h) {
-    int best = -1, tri = -1;
-    float tb = PRT_INF, b1 = 0.0f, b2 = 0.0f;
+#ifndef PT_RES_REGEN_MIN
+#define PT_RES_REGEN_MIN 6        // idle lanes a warp collects before it splats finished paths and starts new ones
+#endif
+
+// nearest hit of the ray (o, d) within [0, tmax] by brute force over the staged scene: analytic primitive `prim` or sorted
+// triangle `tri` (at most one of them >= 0 on return)
+__device__ __forceinline__ bool res_query(const ResScene &R, float3 o, float3 d, float tmax, float &tb, int &prim, int &tri, float &b1,
+                                          float &b2) {
+    prim = -1;
+    tri = -1;
+    tb = tmax;
     for (int i = 0; i < R.n_prims; i++) {
         const float t = intersect_prim(R.prims[i], o, d, tb);
-        if (t >= 0.0f && (best < 0 || t < tb)) { best = i; tb = t; }
+        if (t >= 0.0f && (prim < 0 || t < tb)) { prim = i; tb = t; }
     }
     const RayRows rr = ray_rows(ray_precompute(d));
     for (int j = 0; j < R.n_tris; j++) {
         const float4 *tv = R.tv + 3 * j;
         if (intersect_tri_rows(rr, o, xyz(tv[0]), xyz(tv[1]), xyz(tv[2]), tb, b1, b2)) tri = j;
     }
-    if (tri >= 0) { fill_tri_hit(P.sc, tri, tb, b1, b2, h); return true; }
-    if (best < 0) return false;
-    fill_prim_hit(R.prims[best], best, o, d, tb, h);
-    return true;
+    if (tri >= 0) prim = -1;
+    return prim >= 0 || tri >= 0;
 }
 
-__device__ __forceinline__ bool res_occluded(const ResScene &R, float3 o, float3 d, float tmax) {
-    for (int i = 0; i < R.n_prims; i++)
-        if (intersect_prim(R.prims[i], o, d, tmax) >= 0.0f) return true;
-    const RayRows rr = ray_rows(ray_precompute(d));
-    float tb = tmax, b1, b2;
-    for (int j = 0; j < R.n_tris; j++) {
-        const float4 *tv = R.tv + 3 * j;
-        if (intersect_tri_rows(rr, o, xyz(tv[0]), xyz(tv[1]), xyz(tv[2]), tb, b1, b2)) return true;
-    }
-    return false;
-}
-
+// One loop, one ray query per lane and iteration.  A lane is idle (mode 0: its path is finished, result waiting to be
+// splatted), about to extend its path (mode 1) or about to trace its shadow ray (mode 2).  Both kinds of ray run through
+// the SAME brute-force loop in the same iteration, so the query -- two thirds of all instructions -- executes with nearly
+// full warps; a first version that traced "closest, then shadow" inside one iteration ran the shadow loop with 15 of 32
+// lanes and regenerated / splatted paths 3 to 9 lanes at a time (ncu r02: 16.1 active lanes on average).  Finished lanes
+// wait until PT_RES_REGEN_MIN of them can splat and restart together.
 __global__ void __launch_bounds__(PT_THREADS, PT_RES_MINB) k_render_resident(const PtDev P) {
     __shared__ DPrim sprims[MAX_SMEM_PRIMS];
     __shared__ float4 stri[3 * PT_RES_MAX_TRIS];
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_RES_MINB) k_render_resident(con
     ResScene R;
     R.prims = sprims; R.tv = stri; R.n_prims = P.sc.n_prims; R.n_tris = P.sc.n_tris;
     const int lane = threadIdx.x & 31;
+    const unsigned FULLM = 0xffffffffu;
     PtCounters cn = { 0, 0, 0, 0 };
     const int n_tiles = P.tiles_x * P.tiles_y;
     const unsigned n_items = P.n_s * 256u;
@@ -172,46 +173,61 @@ __global__ void __launch_bounds__(PT_THREADS, PT_RES_MINB) k_render_resident(con
         if (threadIdx.x == 0) s_next = 0u;
         __syncthreads();
         PtState st;
-        bool live = false, dry = false;      // dry: warp-uniform
+        ShadowReq sr;
+        sr.want = false;
+        int mode = 0;
+        bool has_res = false, live_after = false, dry = false;      // dry: warp-uniform
         for (;;) {
-            if (!dry) {
-                const unsigned need = __ballot_sync(0xffffffffu, !live);
-                if (need) {
+            const unsigned idle = __ballot_sync(FULLM, mode == 0);
+            if (idle && (__popc(idle) >= PT_RES_REGEN_MIN || (idle == FULLM))) {
+                if (mode == 0 && has_res) {
+                    pt_splat(P.tent, tile, tx0, ty0, st.px, st.py, st.res);
+                    has_res = false;
+                }
+                if (!dry) {
                     unsigned base = 0u;
-                    if (lane == __ffs(need) - 1) base = atomicAdd(&s_next, (unsigned) __popc(need));
-                    base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
-                    if (!live) {
-                        const unsigned item = base + __popc(need & ((1u << lane) - 1u));
+                    const int leader = __ffs(idle) - 1;
+                    if (lane == leader) base = atomicAdd(&s_next, (unsigned) __popc(idle));
+                    base = __shfl_sync(FULLM, base, leader);
+                    if (mode == 0) {
+                        const unsigned item = base + __popc(idle & ((1u << lane) - 1u));
                         if (item < n_items) {
                             const unsigned j = item >> 8, r = item & 255u, w = r >> 5, l = r & 31u;
                             const int x = tx0 + (int) ((w & 1u) * 8u + (l & 7u)), y = ty0 + (int) ((w >> 1) * 4u + (l >> 3));
                             if (x < P.W && y < P.H) {
                                 pt_init(P, x, y, P.s_offset + j * P.s_stride, st);
                                 cn.paths++;
-                                live = true;
+                                mode = 1;
                             }
                         }
                     }
-                    dry = base + (unsigned) __popc(need) >= n_items;
+                    dry = base + (unsigned) __popc(idle) >= n_items;
                 }
             }
-            if (!__any_sync(0xffffffffu, live)) {
+            if (!__any_sync(FULLM, mode != 0)) {
                 if (dry) break;
                 continue;
             }
-            if (live) {
-                Hit h;
+            if (mode != 0) {
+                const bool ext = mode == 1;
+                const float3 qo = ext ? st.o : sr.o, qd = ext ? st.d : sr.d;
+                float tb, b1 = 0.0f, b2 = 0.0f;
+                int prim, tri;
+                const bool hit = res_query(R, qo, qd, ext ? PRT_INF : sr.tmax, tb, prim, tri, b1, b2);
                 cn.rays++;
-                const bool valid = res_closest(P, R, st.o, st.d, h);
-                if (valid) cn.segments++;
-                ShadowReq sr;
-                live = pt_shade(P, st, h, valid, sr);
-                if (sr.want) {
-                    cn.rays++;
+                if (ext) {
+                    Hit h;
+                    if (tri >= 0) fill_tri_hit(P.sc, tri, tb, b1, b2, h);
+                    else if (prim >= 0) fill_prim_hit(R.prims[prim], prim, qo, qd, tb, h);
+                    if (hit) cn.segments++;
+                    live_after = pt_shade(P, st, h, hit, sr);
+                    mode = sr.want ? 2 : (live_after ? 1 : 0);
+                } else {
                     cn.shadow++;
-                    if (!res_occluded(R, sr.o, sr.d, sr.tmax)) pt_apply_shadow(st, sr);
+                    if (!hit) pt_apply_shadow(st, sr);
+                    mode = live_after ? 1 : 0;
                 }
-                if (!live) pt_splat(P.tent, tile, tx0, ty0, st.px, st.py, st.res);
+                has_res = mode == 0;
             }
         }
         __syncthreads();
@@ -285,6 +301,8 @@ static int fill_pt(prt_scene *s, const prt_render_params *p, uint64_t seed, uint
     P.tiles_y = (p->height + PT_TILE - 1) / PT_TILE;
     P.film = nullptr;
     P.stats = nullptr;
+    P.box_lo = make_float3(s->stats.scene_lo[0], s->stats.scene_lo[1], s->stats.scene_lo[2]);
+    P.box_hi = make_float3(s->stats.scene_hi[0], s->stats.scene_hi[1], s->stats.scene_hi[2]);
     return PRT_OK;
 }
 
@@ -302,6 +320,10 @@ static int launch_pt(prt_context *c, const PtDev &P, cudaStream_t st) {
     else if (mode && mode[0] == 'w') which = 1;
     else if (mode && mode[0] == 'r') which = 2;
     if (which == 2 && !fits) { set_error("render_path: PRT_PT_MODE=resident needs <= 64 primitives and <= 64 triangles"); return PRT_ERR_INVALID; }
+    // The wavefront enqueues ~4 kernels per bounce for max_depth bounces without ever reading a queue length back; Mitsuba's
+    // default max_depth = -1 (unbounded, mapped to 2^20 by the plugin) would be millions of empty launches.  Paths of
+    // unbounded depth end by Russian roulette: the per-lane loop of the megakernel handles them naturally.
+    if (which == 1 && P.max_depth > 64) which = 0;
     if (which == 1) return launch_wavefront(c, P, st);
     const void *kern = which == 2 ? (const void *) k_render_resident : (const void *) k_render_path;
     int per_sm = 0;

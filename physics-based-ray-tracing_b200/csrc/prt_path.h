@@ -17,6 +17,7 @@ struct PtDev {
     uint32_t spp_total, s_offset, s_stride, n_s;
     int tiles_x, tiles_y;
     unsigned kind_mask;          // bit k set iff some material has kind k (PRT_MAT_*)
+    float3 box_lo, box_hi;       // bounds of the triangle geometry (ray-sort cells, prt_wavefront.cu)
     float *film;                 // [H][W][4]
     unsigned long long *stats;   // {paths, segments, rays, shadow_rays}
 };

@@ -1,6 +1,7 @@
 // prt_scene.cu -- context + scene container behind the C ABI: host-side assembly of analytic primitives,
 // materials and world-space triangle soup, upload to device-resident float4 SoA buffers, LBVH build.
 // Replaces mi.set_variant / mi.load_dict / mi.traverse(...).update() (/root/reference/USMain.py:12,257-265).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -100,6 +101,7 @@ prt::DScene prt_scene::view() const {
     v.n_prims = (int) prims.size();
     v.n_mats = (int) mats.size();
     v.n_tris = (int) n_tris;
+    v.n_small = (int) n_small;
     v.root_ref = root_ref;
     v.em_tri = em_tri_dev;
     v.em_first = em_first_dev;
@@ -405,6 +407,22 @@ __global__ void k_gather_aux(const uint32_t *__restrict__ order, uint32_t n, con
     }
 }
 
+}  // extern "C"
+
+namespace prt {
+// oversized triangles (DScene::n_small): v1.w = bits((sorted index << 2) | shading queue), as k_bvh8_annotate stamps the BVH8 copies
+__global__ void k_annotate_big(uint32_t first, uint32_t end, const int4 *__restrict__ tri_info, const DMaterial *__restrict__ mats,
+                               float4 *__restrict__ tri_v) {
+    const uint32_t i = first + threadIdx.x;
+    if (i >= end) return;
+    const int kind = mats[tri_info[i].z].kind;
+    const uint32_t qi = kind == PRT_MAT_DIFFUSE ? 0u : (kind == PRT_MAT_DIELECTRIC ? 1u : 2u);
+    tri_v[3 * (size_t) i + 1].w = __uint_as_float((i << 2) | qi);
+}
+}  // namespace prt
+
+extern "C" {
+
 int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
     PRT_REQUIRE(s, "prt_scene_commit: null scene");
     std::lock_guard<std::mutex> lk(s->ctx->mtx);
@@ -431,6 +449,7 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
     }
     PRT_REQUIRE(nt < (1ull << 29), "prt_scene_commit: too many triangles (limit 2^29)");
     s->n_tris = (uint32_t) nt;
+    s->n_small = 0;
     s->root_ref = -1;
     if (nt) {
         // host staging in input order: float4 vertices, int4 info, float4 normals
@@ -448,6 +467,65 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
                 hi[o] = make_int4((int) o, m.shape, m.material, (m.has_n ? 1 : 0) | (m.flip ? 2 : 0));
             }
         }
+        // Oversized triangles (bounding-box area > 1024 x the mean; at most 64, largest first) can be moved to the END of the
+        // staging arrays and kept out of the hierarchy (DScene::n_small): PRT_BIG_TRIS=1.  OFF by default -- measured on
+        // B200 (profiles/r02_summary.md): on the 10 M-triangle height field the tree gets 35 % cheaper by absolute SAH cost,
+        // but the twelve brute-force tests run when a lane fetches its ray, i.e. with 2-4 active lanes per warp, and the
+        // closest-hit kernel goes from 81 to 108 ms per step.
+        float blo[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, bhi[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
+        uint64_t n_big = 0;
+        {
+            std::vector<float> area(nt);
+            double sum = 0.0;
+            for (uint64_t t = 0; t < nt; t++) {
+                float lo[3], hi[3];
+                for (int k = 0; k < 3; k++) {
+                    const float a = (&hv[3 * t].x)[k], b = (&hv[3 * t + 1].x)[k], c = (&hv[3 * t + 2].x)[k];
+                    lo[k] = std::min(a, std::min(b, c));
+                    hi[k] = std::max(a, std::max(b, c));
+                    blo[k] = std::min(blo[k], lo[k]);
+                    bhi[k] = std::max(bhi[k], hi[k]);
+                }
+                const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+                area[t] = ex * ey + ey * ez + ez * ex;
+                sum += area[t];
+            }
+            const char *e = getenv("PRT_BIG_TRIS");
+            const bool enabled = e && e[0] == '1' && nt > 64;
+            const float limit = (float) (1024.0 * sum / (double) nt);
+            std::vector<uint64_t> big;
+            if (enabled)
+                for (uint64_t t = 0; t < nt; t++)
+                    if (area[t] > limit) big.push_back(t);
+            if (big.size() > 64) {
+                std::partial_sort(big.begin(), big.begin() + 64, big.end(), [&](uint64_t a, uint64_t b) { return area[a] > area[b]; });
+                big.resize(64);
+                std::sort(big.begin(), big.end());
+            }
+            n_big = big.size();
+            if (n_big) {
+                std::vector<char> is_big(nt, 0);
+                for (uint64_t t : big) is_big[t] = 1;
+                std::vector<float4> v2(nt * 3), n2(any_n ? nt * 3 : 0);
+                std::vector<int4> i2(nt);
+                uint64_t w = 0;
+                for (int pass = 0; pass < 2; pass++)
+                    for (uint64_t t = 0; t < nt; t++)
+                        if ((int) is_big[t] == pass) {
+                            for (int c = 0; c < 3; c++) {
+                                v2[3 * w + c] = hv[3 * t + c];
+                                if (any_n) n2[3 * w + c] = hn[3 * t + c];
+                            }
+                            i2[w] = hi[t];          // .x keeps the ORIGINAL triangle index (what prt_trace_closest reports)
+                            w++;
+                        }
+                hv.swap(v2);
+                hn.swap(n2);
+                hi.swap(i2);
+            }
+        }
+        const uint64_t n_small = nt - n_big;
+        s->n_small = (uint32_t) n_small;
         float4 *v_in = nullptr, *n_in = nullptr;
         int4 *i_in = nullptr;
         uint32_t *order = nullptr;
@@ -467,18 +545,36 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
         PRT_CUDA(cudaMalloc(&s->nodes_dev, sizeof(float4) * 4 * (nt > 1 ? nt - 1 : 1)));
         bytes += sizeof(float4) * 3 * nt + sizeof(int4) * nt + sizeof(float4) * 4 * (nt > 1 ? nt - 1 : 1);
         Bvh8Out b8;
-        int rc = build_lbvh(s->ctx, v_in, (uint32_t) nt, s->tri_v_dev, order, s->nodes_dev, &s->root_ref, &s->stats, st, &b8);
+        int rc = build_lbvh(s->ctx, v_in, (uint32_t) n_small, s->tri_v_dev, order, s->nodes_dev, &s->root_ref, &s->stats, st, &b8);
         if (rc) return rc;
+        if (n_big) {       // the oversized triangles keep their staging order behind the sorted ones; k_gather_tris's stamp (v0.w = source index)
+            std::vector<uint32_t> tail(n_big);
+            for (uint64_t j = 0; j < n_big; j++) {
+                tail[j] = (uint32_t) (n_small + j);
+                hv[3 * (n_small + j)].w = __int_as_float_host((int) (n_small + j));
+            }
+            PRT_CUDA(cudaMemcpyAsync(order + n_small, tail.data(), sizeof(uint32_t) * n_big, cudaMemcpyHostToDevice, st));
+            PRT_CUDA(cudaMemcpyAsync(s->tri_v_dev + 3 * n_small, hv.data() + 3 * n_small, sizeof(float4) * 3 * n_big, cudaMemcpyHostToDevice, st));
+            PRT_CUDA(cudaStreamSynchronize(st));
+        }
+        for (int k = 0; k < 3; k++) {       // bounds of ALL triangles (build_lbvh reported the hierarchy's)
+            s->stats.scene_lo[k] = blo[k];
+            s->stats.scene_hi[k] = bhi[k];
+        }
         s->nodes8_dev = b8.nodes8;
         s->tri_v8_dev = b8.tri_v8;
         s->tri8_sorted_dev = b8.tri8_sorted;
         s->n_nodes8 = b8.n_nodes8;
         s->bvh8_levels = b8.levels;
         s->bvh8_build_ms = b8.build_ms;
-        if (b8.n_nodes8) bytes += sizeof(float4) * 5 * (size_t) b8.n_nodes8 + (sizeof(float4) * 3 + sizeof(uint32_t)) * nt;
+        if (b8.n_nodes8) bytes += sizeof(float4) * 5 * (size_t) b8.n_nodes8 + (sizeof(float4) * 3 + sizeof(uint32_t)) * n_small;
         k_gather_aux<<<(unsigned) ((nt + 255) / 256), 256, 0, st>>>(order, (uint32_t) nt, i_in, n_in, s->tri_info_dev, s->tri_n_dev);
-        rc = bvh8_annotate((uint32_t) nt, s->tri8_sorted_dev, s->tri_info_dev, s->mats_dev, s->tri_v8_dev, st);
+        rc = bvh8_annotate((uint32_t) n_small, s->tri8_sorted_dev, s->tri_info_dev, s->mats_dev, s->tri_v8_dev, st);
         if (rc) return rc;
+        if (n_big) {
+            k_annotate_big<<<1, 64, 0, st>>>((uint32_t) n_small, (uint32_t) nt, s->tri_info_dev, s->mats_dev, s->tri_v_dev);
+            PRT_CUDA(cudaGetLastError());
+        }
         PRT_CUDA(cudaStreamSynchronize(st));
         PRT_CUDA(cudaGetLastError());
         cudaFree(v_in);
@@ -531,7 +627,7 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
     s->stats.n_nodes8 = s->n_nodes8;
     s->stats.bvh8_levels = (uint32_t) s->bvh8_levels;
     s->stats.bvh8_build_ms = s->bvh8_build_ms;
-    s->stats._pad = 0.0f;
+    s->stats.n_oversized = s->n_tris - s->n_small;
     s->committed = true;
     if (out) *out = s->stats;
     return PRT_OK;

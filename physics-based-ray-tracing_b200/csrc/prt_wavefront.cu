@@ -28,6 +28,7 @@
 // bounce, zeroed once), so the host never synchronises inside a batch.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "prt_bvh8.cuh"
@@ -107,6 +108,7 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 //   r3 = Sx, Sy, Sz, bits(kx | ky << 2 | kz << 4)     (ray_precompute: watertight triangle test)
 struct WfRays {
     float4 *r0, *r1, *r2, *r3;
+    uint32_t *key;   // sort key of the ray (origin cell | direction octant), nullptr when ray sorting is off
 };
 
 struct WfBuf {
@@ -123,6 +125,10 @@ struct WfBuf {
     uint8_t *tag;    // [cap] per slot: 1 + shading queue of the hit waiting to be shaded, 0 = nothing to shade
     int *cnt;        // [bounces + 1][WF_CSTRIDE]
     uint32_t cap, L, n_layers, j0;
+    // ray sorting (big scenes): key = Morton code of the origin's cell (sort_bits per axis over the scene box) and the
+    // direction octant; rays are traced in key order through a permutation of the queue positions
+    int sort_bits, sort_mode;            // bits per axis (0 = off); mode 0: cell major, octant minor; 1: octant major
+    float3 key_lo, key_scale;
 };
 
 // analytic primitives staged in shared memory by the trace kernels (all of them, or none if there are too many)
@@ -148,7 +154,27 @@ __device__ __forceinline__ int wf_reserve(int *counter, bool pred) {
     return pred ? base + __popc(m & lanemask_lt()) : -1;
 }
 
-__device__ __forceinline__ void wf_write_ray(const WfRays &R, int pos, float3 o, float3 d, float tmax, uint32_t slot, float extra) {
+__device__ __forceinline__ uint32_t wf_part1by2(uint32_t x) {      // 10 bits -> every third bit
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t wf_ray_key(const WfBuf &B, float3 o, float3 d) {
+    const float top = (float) ((1 << B.sort_bits) - 1);
+    const uint32_t ix = (uint32_t) fminf(fmaxf((o.x - B.key_lo.x) * B.key_scale.x, 0.0f), top);
+    const uint32_t iy = (uint32_t) fminf(fmaxf((o.y - B.key_lo.y) * B.key_scale.y, 0.0f), top);
+    const uint32_t iz = (uint32_t) fminf(fmaxf((o.z - B.key_lo.z) * B.key_scale.z, 0.0f), top);
+    const uint32_t cell = (wf_part1by2(ix) << 2) | (wf_part1by2(iy) << 1) | wf_part1by2(iz);
+    const uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
+    return B.sort_mode ? (oct << (3 * B.sort_bits)) | cell : (cell << 3) | oct;
+}
+
+__device__ __forceinline__ void wf_write_ray(const WfBuf &B, const WfRays &R, int pos, float3 o, float3 d, float tmax, uint32_t slot, float extra) {
+    if (R.key) R.key[pos] = wf_ray_key(B, o, d);
     const RayPre rp = ray_precompute(d);
     const Bvh8Ray r8 = bvh8_ray(o, d);
     st_stream(R.r0 + pos, make_float4(o.x, o.y, o.z, __uint_as_float(slot)));
@@ -215,7 +241,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_generate(const PtDev P,
             made++;
         }
         const int q = wf_reserve(B.cnt + C_EXT, inside);
-        if (inside) wf_write_ray(B.ext[0], q, st.o, st.d, PRT_INF, slot, 0.0f);
+        if (inside) wf_write_ray(B, B.ext[0], q, st.o, st.d, PRT_INF, slot, 0.0f);
     }
     wf_add_stat(P, 0, made);
 }
@@ -223,8 +249,12 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_generate(const PtDev P,
 // ------------------------------------------------------------------------------------------------------------------
 // ray queries with dynamic fetch over the compressed 8-wide BVH
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef WF_TOPN
+#define WF_TOPN 0                         // first WF_TOPN nodes of the 8-wide BVH (breadth-first: 73 = top three levels) staged in shared memory
+#endif
 template <bool ANY>
-__global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(const PtDev P, const WfBuf B, const int bounce) {
+__global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(const PtDev P, const WfBuf B, const int bounce,
+                                                                              const uint32_t *__restrict__ perm) {
     // dynamic shared memory: [analytic primitives (n_prims x 128 B; none for pure mesh scenes, which leaves that much more
     // of the SM's unified array to L1)][optionally the first WF_SSTACK traversal-stack entries of every lane, entry-major].
     // The stack in local memory misses L1 on 89 % of the pops (ncu r01), yet moving it to shared memory bought nothing
@@ -235,6 +265,15 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
     uint2 *sstack = reinterpret_cast<uint2 *>(s_dyn + (sc_n_smem_prims(P.sc) * (int) (sizeof(DPrim) / 16))) + threadIdx.x;
     __shared__ int s_owner[WF_TRACE_THREADS], s_win[WF_TRACE_THREADS];
     __shared__ unsigned s_tmin[WF_TRACE_THREADS];
+#if WF_TOPN
+    // The top levels are fetched by every ray of every warp.  They hit in L1 anyway (ncu r01: top of the tree is < 6 KB), so
+    // staging them is worth one L1 -> shared latency difference per visit, nothing more: measured in profiles/r02_summary.md
+    __shared__ float4 s_top[5 * WF_TOPN];
+    {
+        const int ntop = min(WF_TOPN, P.sc.n_nodes8);
+        for (int i = threadIdx.x; i < 5 * ntop; i += blockDim.x) s_top[i] = P.sc.nodes8[i];
+    }
+#endif
 #if WF_QCHUNK
     // warp-private cursors into the shading queues: a warp reserves WF_QCHUNK entries per atomic and fills them over
     // several retire events, so retiring a ray does not wait for a round trip to the L2 atomic unit
@@ -369,7 +408,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                 const int rank = __popc(need & lanemask_lt());
                 const bool take = !has && rank < avail;
                 if (take) {
-                    qpos = (uint32_t) (pool_next + rank);
+                    qpos = perm ? __ldg(perm + pool_next + rank) : (uint32_t) (pool_next + rank);
                     const float4 a = ld_stream(R.r0 + qpos), c2 = ld_stream(R.r2 + qpos), c3 = ld_stream(R.r3 + qpos);
                     r8.o = xyz(a);
                     slot = __float_as_uint(a.w);
@@ -400,9 +439,28 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                         }
                         if (!ANY) tbest = prim_t;
                     }
+                    if (sc.n_small < sc.n_tris && !blocked) {
+                        // the scene's oversized triangles (DScene::n_small) are not in the hierarchy: test them here, one by
+                        // one; the traversal below then starts with their nearest hit as its bound
+#if PRT_TRI_ROWS
+                        const RayRows rr = ray_rows(rp);
+#endif
+                        for (int j = sc.n_small; j < sc.n_tris; j++) {
+                            const float4 *tv = sc.tri_v + 3 * (size_t) j;
+                            const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
+#if PRT_TRI_ROWS
+                            if (intersect_tri_rows(rr, r8.o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#else
+                            if (intersect_tri_wt(rp, r8.o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#endif
+                                best = __float_as_int(b.w);
+                                if (ANY) { blocked = true; break; }
+                            }
+                        }
+                    }
                     sp = 0;
                     ng = make_uint2(0u, 0x80000000u);
-                    busy = !(sc.n_tris == 0 || blocked);
+                    busy = !(sc.n_small == 0 || blocked);
                 }
                 pool_next += min(avail, __popc(need));
                 need = __ballot_sync(FULL, !has);
@@ -424,7 +482,13 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
             const uint32_t slot_index = (uint32_t) (bit - 24) ^ (r8.octinv4 & 0xffu);
             const uint32_t rel = __popc(imask8 & ~(0xffffffffu << slot_index));
             uint32_t child_base, tri_base, imask;
+#if WF_TOPN
+            const uint32_t nidx = ng.x + rel;
+            const uint32_t hm = nidx < (uint32_t) WF_TOPN ? bvh8_node<true>(s_top, nidx, r8, tbest, child_base, tri_base, imask)
+                                                           : bvh8_node(sc.nodes8, nidx, r8, tbest, child_base, tri_base, imask);
+#else
             const uint32_t hm = bvh8_node(sc.nodes8, ng.x + rel, r8, tbest, child_base, tri_base, imask);
+#endif
             ng = make_uint2(child_base, (hm & 0xff000000u) | imask);
             tg = make_uint2(tri_base, hm & 0x00ffffffu);
 #if WF_PREFETCH & 4
@@ -558,6 +622,108 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// ray sorting: LSD radix sort of (key, queue position) with 8-bit digits; the number of rays lives in device memory
+// (the queue counter), so every kernel is launched for the batch capacity and blocks past the end do nothing
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int RQ_THREADS = 256, RQ_ITEMS = 8, RQ_TILE = RQ_THREADS * RQ_ITEMS;
+
+__global__ void __launch_bounds__(RQ_THREADS) k_rq_hist(const uint32_t *__restrict__ keys, const int *__restrict__ n_dev, int shift,
+                                                        uint32_t *__restrict__ hist, uint32_t nblocks) {
+    __shared__ uint32_t h[256];
+    const uint32_t n = (uint32_t) *n_dev;
+    const uint32_t base = blockIdx.x * RQ_TILE;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    if (base < n) {
+#pragma unroll
+        for (int i = 0; i < RQ_ITEMS; i++) {
+            const uint32_t idx = base + i * RQ_THREADS + threadIdx.x;
+            if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+    }
+    hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// vals_in == nullptr: the value of element i is i (first pass)
+__global__ void __launch_bounds__(RQ_THREADS) k_rq_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                                                           uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                           const int *__restrict__ n_dev, int shift, const uint32_t *__restrict__ hist,
+                                                           uint32_t nblocks) {
+    __shared__ uint32_t wh[RQ_THREADS / 32][256];
+    const uint32_t n = (uint32_t) *n_dev;
+    if (blockIdx.x * RQ_TILE >= n) return;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = lane; j < 256; j += 32) wh[w][j] = 0;
+    __syncwarp();
+    const uint32_t base = blockIdx.x * RQ_TILE + w * (RQ_ITEMS * 32);
+    uint32_t key[RQ_ITEMS], off[RQ_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RQ_ITEMS; i++) {
+        const uint32_t idx = base + i * 32 + lane;
+        const bool ok = idx < n;
+        key[i] = ok ? keys_in[idx] : 0xffffffffu;
+        const uint32_t digit = ok ? ((key[i] >> shift) & 255u) : 256u;
+        const uint32_t peers = __match_any_sync(FULL, digit);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        const int leader = __ffs(peers) - 1;
+        uint32_t pre = 0;
+        if (ok && lane == leader) {
+            pre = wh[w][digit];
+            wh[w][digit] = pre + __popc(peers);
+        }
+        pre = __shfl_sync(FULL, pre, leader);
+        off[i] = pre + rank;
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const uint32_t d = threadIdx.x;
+        uint32_t running = hist[d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < RQ_THREADS / 32; ww++) {
+            const uint32_t c = wh[ww][d];
+            wh[ww][d] = running;
+            running += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RQ_ITEMS; i++) {
+        const uint32_t idx = base + i * 32 + lane;
+        if (idx < n) {
+            const uint32_t pos = wh[w][(key[i] >> shift) & 255u] + off[i];
+            keys_out[pos] = key[i];
+            vals_out[pos] = vals_in ? vals_in[idx] : idx;
+        }
+    }
+}
+
+struct WfSort {
+    uint32_t *keys[2], *vals[2], *hist, *scan;
+    uint32_t nblocks;
+    int passes;
+};
+
+// sorts the first *n_dev entries of `keys`; returns the permutation (sorted rank -> queue position) in *perm
+static int wf_sort(const WfSort &S, const uint32_t *keys, const int *n_dev, const uint32_t **perm, cudaStream_t st, int *launches) {
+    const uint32_t *kin = keys, *vin = nullptr;
+    int cur = 0;
+    for (int pass = 0; pass < S.passes; pass++) {
+        k_rq_hist<<<S.nblocks, RQ_THREADS, 0, st>>>(kin, n_dev, 8 * pass, S.hist, S.nblocks);
+        exclusive_scan_u32(S.hist, 256 * S.nblocks, S.scan, st);
+        k_rq_scatter<<<S.nblocks, RQ_THREADS, 0, st>>>(kin, vin, S.keys[cur], S.vals[cur], n_dev, 8 * pass, S.hist, S.nblocks);
+        kin = S.keys[cur];
+        vin = S.vals[cur];
+        cur ^= 1;
+        *launches += 5;
+    }
+    *perm = vin;
+    PRT_CUDA(cudaGetLastError());
+    return PRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // shading, one kernel per material queue
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef WF_SHADE0_MINB
@@ -646,10 +812,10 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, QI == 0 ? WF_SHADE0_MINB : W
         const int j = (int) (base2 & 0xffffffffull) + __popc(m_sh & lanemask_lt());
         const int e = (int) (base2 >> 32) + __popc(m_ex & lanemask_lt());
         if (sr.want) {
-            wf_write_ray(B.sh, j, sr.o, sr.d, sr.tmax, slot, sr.w);
+            wf_write_ray(B, B.sh, j, sr.o, sr.d, sr.tmax, slot, sr.w);
             st_stream(B.SHC + j, make_float4(sr.c.x, sr.c.y, sr.c.z, 0.0f));
         }
-        if (live) wf_write_ray(Rn, e, st.o, st.d, PRT_INF, slot, 0.0f);
+        if (live) wf_write_ray(B, Rn, e, st.o, st.d, PRT_INF, slot, 0.0f);
     }
 }
 
@@ -686,7 +852,7 @@ static int wf_grid(prt_context *c, const void *kernel, int threads, int *grid, s
 }
 
 int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
-    PRT_REQUIRE(P.sc.n_tris == 0 || P.sc.n_nodes8 > 0, "render_path (wavefront): the scene has no 8-wide BVH");
+    PRT_REQUIRE(P.sc.n_small == 0 || P.sc.n_nodes8 > 0, "render_path (wavefront): the scene has no 8-wide BVH");
     const uint32_t n_tiles = (uint32_t) P.tiles_x * (uint32_t) P.tiles_y;
     const uint64_t L = (uint64_t) n_tiles * 256u;
     uint64_t batch = 1ull << 25;      // 2^25 path slots = 11.7 GB of state + queues (measured: cbox +1 % over 2^24, -8 % at 2^22)
@@ -701,10 +867,27 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
     PRT_REQUIRE(cap < (1ull << 31), "render_path (wavefront): batch too large");
     const int bounces = P.max_depth > 1 ? P.max_depth : 1;
     const size_t cnt_bytes = (sizeof(int) * (WF_CSTRIDE * (size_t) (bounces + 1) + 2) + 255) & ~(size_t) 255;
-    const size_t per_slot = 16 * (8 + 8 + 4 + 1) + 4 * WF_QUEUES;
+    // ---- run-time knobs of the big-scene path ----
+    //   PRT_WF_SORT=<bits per axis>  sort every bounce's rays by (origin cell, direction octant).  PRT_WF_SORT_MODE=1: octant
+    //                                major.  PRT_WF_SORT_WHAT: bit 0 extend rays, bit 1 shadow rays (default 3).  OFF by
+    //                                default: measured on the 10 M-triangle height field (profiles/r02_summary.md) the sorted
+    //                                closest-hit launches are 2 % faster, the shadow launches 8 %, and the sorts themselves
+    //                                cost 8 % of the step -- a diffuse bounce's rays share an origin cell, not a destination.
+    //   PRT_L2_PERSIST_MB=<MB>       access-policy window over the 8-wide BVH nodes (persisting L2 lines)
+    auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; };
+    int sort_bits = env_int("PRT_WF_SORT", 0);
+    if (sort_bits > 9) sort_bits = 9;                      // 3 x 9 cell bits + 3 octant bits = 30-bit keys
+    if (sort_bits < 0 || P.sc.n_tris == 0) sort_bits = 0;
+    const int sort_mode = env_int("PRT_WF_SORT_MODE", 0), sort_what = sort_bits ? env_int("PRT_WF_SORT_WHAT", 3) : 0;
+    const size_t per_slot = 16 * (8 + 8 + 4 + 1) + 4 * WF_QUEUES + (sort_bits ? 4 * 6 : 0);
+    WfSort S;
+    S.nblocks = (uint32_t) ((cap + RQ_TILE - 1) / RQ_TILE);
+    S.passes = (3 * sort_bits + 3 + 7) / 8;
+    const size_t hist_words = 256 * (size_t) S.nblocks, scan_words = hist_words / 2048 + 8192;
+    const size_t sort_bytes = sort_bits ? 4 * (hist_words + scan_words) + 256 : 0;
     // every trace warp may leave one partly used chunk per queue behind (holes): room for them on top of `cap` entries
     const size_t q_slack = (size_t) c->sm_count * 64 * (WF_QCHUNK ? WF_QCHUNK : 1);
-    const size_t need = (size_t) cap * (per_slot + 1) + 4 * WF_QUEUES * q_slack + cnt_bytes;
+    const size_t need = (size_t) cap * (per_slot + 1) + 4 * WF_QUEUES * q_slack + cnt_bytes + sort_bytes;
     if (need > c->wf_cap) {
         if (c->wf_dev) cudaFree(c->wf_dev);
         c->wf_dev = nullptr;
@@ -717,13 +900,53 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
         char *p = reinterpret_cast<char *>(c->wf_dev);
         auto take = [&](size_t bytes) { char *r = p; p += bytes; return r; };
         auto take4 = [&]() { return reinterpret_cast<float4 *>(take(16 * cap)); };
+        auto take1 = [&]() { return reinterpret_cast<uint32_t *>(take(4 * cap)); };
         B.cnt = reinterpret_cast<int *>(take(cnt_bytes)) + 1;      // odd int offset: see the counter layout above
         B.ST = reinterpret_cast<float4 *>(take(128 * cap));
-        for (int k = 0; k < 2; k++) { B.ext[k].r0 = take4(); B.ext[k].r1 = take4(); B.ext[k].r2 = take4(); B.ext[k].r3 = take4(); }
-        B.sh.r0 = take4(); B.sh.r1 = take4(); B.sh.r2 = take4(); B.sh.r3 = take4();
+        for (int k = 0; k < 2; k++) { B.ext[k].r0 = take4(); B.ext[k].r1 = take4(); B.ext[k].r2 = take4(); B.ext[k].r3 = take4(); B.ext[k].key = nullptr; }
+        B.sh.r0 = take4(); B.sh.r1 = take4(); B.sh.r2 = take4(); B.sh.r3 = take4(); B.sh.key = nullptr;
         B.SHC = take4();
         for (int k = 0; k < WF_QUEUES; k++) B.q_mat[k] = reinterpret_cast<uint32_t *>(take(4 * (cap + q_slack)));
         B.tag = reinterpret_cast<uint8_t *>(take(cap));
+        if (sort_bits) {
+            p = reinterpret_cast<char *>(((uintptr_t) p + 255) & ~(uintptr_t) 255);
+            // one key array serves both extend-ray buffers: the keys shading writes for bounce b + 1 are consumed by the
+            // sort at the start of bounce b + 1, before shading writes the next set
+            uint32_t *kext = take1();
+            if (sort_what & 1) B.ext[0].key = B.ext[1].key = kext;
+            uint32_t *ksh = take1();
+            if (sort_what & 2) B.sh.key = ksh;
+            S.keys[0] = take1(); S.keys[1] = take1(); S.vals[0] = take1(); S.vals[1] = take1();
+            S.hist = reinterpret_cast<uint32_t *>(take(4 * hist_words));
+            S.scan = reinterpret_cast<uint32_t *>(take(4 * scan_words));
+        }
+    }
+    B.sort_bits = sort_bits;
+    B.sort_mode = sort_mode;
+    {
+        const float cells = (float) (1 << (sort_bits ? sort_bits : 1));
+        const float3 ext = make_float3(P.box_hi.x - P.box_lo.x, P.box_hi.y - P.box_lo.y, P.box_hi.z - P.box_lo.z);
+        B.key_lo = P.box_lo;
+        B.key_scale = make_float3(ext.x > 0.0f ? cells / ext.x : 0.0f, ext.y > 0.0f ? cells / ext.y : 0.0f, ext.z > 0.0f ? cells / ext.z : 0.0f);
+    }
+    const int l2_mb = env_int("PRT_L2_PERSIST_MB", 0);
+    bool l2_window = false;
+    if (l2_mb > 0 && P.sc.n_nodes8 > 0) {
+        size_t want = (size_t) l2_mb << 20;
+        if (want > (size_t) c->prop.persistingL2CacheMaxSize) want = (size_t) c->prop.persistingL2CacheMaxSize;
+        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            size_t bytes = (size_t) P.sc.n_nodes8 * 80;
+            if (bytes > (size_t) c->prop.accessPolicyMaxWindowSize) bytes = (size_t) c->prop.accessPolicyMaxWindowSize;
+            av.accessPolicyWindow.base_ptr = const_cast<float4 *>(P.sc.nodes8);
+            av.accessPolicyWindow.num_bytes = bytes;
+            av.accessPolicyWindow.hitRatio = bytes > want ? (float) want / (float) bytes : 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            l2_window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+        }
+        cudaGetLastError();
     }
     B.cap = (uint32_t) cap;
     B.L = (uint32_t) L;
@@ -750,9 +973,16 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
             launches++;
         }
         for (int b = 0; b < bounces; b++) {
+            const uint32_t *perm = nullptr;
+            if ((sort_what & 1) && b > 0) {        // camera rays (b == 0) come out of k_wf_generate tile by tile: coherent as they are
+                ProfScope ps(c, PRT_KC_OTHER, st);
+                const int before = launches;
+                if ((rc = wf_sort(S, B.ext[b & 1].key, B.cnt + b * WF_CSTRIDE + C_EXT, &perm, st, &launches))) return rc;
+                ps.kernels = launches - before;
+            }
             {
                 ProfScope ps(c, PRT_KC_TRACE_CLOSEST, st);
-                k_wf_trace<false><<<g_ext, WF_TRACE_THREADS, trace_smem, st>>>(P, B, b);
+                k_wf_trace<false><<<g_ext, WF_TRACE_THREADS, trace_smem, st>>>(P, B, b, perm);
                 launches++;
             }
             {
@@ -767,8 +997,15 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
                 ps.kernels = launches - before;
             }
             if (b + 1 < P.max_depth && (P.kind_mask & (1u << PRT_MAT_DIFFUSE)) && P.sc.n_emitters > 0) {
+                perm = nullptr;
+                if (sort_what & 2) {
+                    ProfScope ps(c, PRT_KC_OTHER, st);
+                    const int before = launches;
+                    if ((rc = wf_sort(S, B.sh.key, B.cnt + b * WF_CSTRIDE + C_SH, &perm, st, &launches))) return rc;
+                    ps.kernels = launches - before;
+                }
                 ProfScope ps(c, PRT_KC_TRACE_SHADOW, st);
-                k_wf_trace<true><<<g_sh, WF_TRACE_THREADS, trace_smem, st>>>(P, B, b);
+                k_wf_trace<true><<<g_sh, WF_TRACE_THREADS, trace_smem, st>>>(P, B, b, perm);
                 launches++;
             }
         }
@@ -787,6 +1024,12 @@ int launch_wavefront(prt_context *c, const PtDev &P, cudaStream_t st) {
                         h[b * WF_CSTRIDE + C_EXT], h[b * WF_CSTRIDE + C_SH], h[b * WF_CSTRIDE + C_MAT], h[b * WF_CSTRIDE + C_MAT + 1],
                         h[b * WF_CSTRIDE + C_MAT + 2]);
         }
+    }
+    if (l2_window) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);      // num_bytes = 0 disables the window
+        cudaCtxResetPersistingL2Cache();
     }
     c->last_launches = launches;
     return PRT_OK;

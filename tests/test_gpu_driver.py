@@ -1,8 +1,11 @@
 """GPU: the reference driver's call sequence (/root/reference/USMain.py:12-24,92-224,257-289) through the
 stand-in packages, and the DAS beamformer ("next" row f1) against a numpy / scipy restatement."""
+import os
+
 import numpy as np
 import pytest
 
+from conftest import ROOT
 from prt_b200 import scenes
 
 pytestmark = pytest.mark.gpu
@@ -219,3 +222,37 @@ def test_usmain_call_sequence():
     assert np.isfinite(f0) and np.isfinite(f1)
     assert f1 < f0           # same seed, same roughness as the reference render (0.7) -> identical image
     assert f1 == 0.0
+
+
+def _reference_dir():
+    """Where a copy of the reference's scripts can be found: the build container mounts /root/reference; on a GPU box it only
+    exists if the operator shipped one (PRT_REFERENCE_DIR, or the git-ignored .scratch_ref/ next to the repo's files -- the
+    reference's sources are never committed)."""
+    for d in (os.environ.get("PRT_REFERENCE_DIR"), "/root/reference", os.path.join(ROOT, ".scratch_ref")):
+        if d and os.path.isfile(os.path.join(d, "USMain.py")):
+            return d
+    return None
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_reference_dir() is None, reason="no copy of the reference's USMain.py on this box")
+def test_unmodified_usmain_runs_to_completion(tmp_path):
+    """/root/reference/USMain.py, byte for byte, to its last line on a GPU (USMain.py:256-298): the reference image, then 25
+    finite-difference iterations x 2 forwards = 51 acquisitions + 51 beamforming passes, and the printed loss trace."""
+    import json
+    import subprocess
+    import sys
+    timing = tmp_path / "timing.json"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_reference_script.py"),
+                        os.path.join(_reference_dir(), "USMain.py"), "--timing", str(timing)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    iters = [l for l in r.stdout.splitlines() if l.startswith("iter ")]
+    assert len(iters) == 25 and iters[0].startswith("iter 0: loss=") and "Final Roughness Value:" in r.stdout
+    rough = [float(l.split("rough=")[1]) for l in iters]
+    assert all(1e-4 <= x <= 1.0 for x in rough)
+    t = json.load(open(timing))
+    assert t["simulate_acquisition_parallel_ms"]["calls"] == 51 and t["beamform_ms"]["calls"] == 51
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "usmain_gpu.json"), "w") as f:
+            json.dump({"timing": t, "loss_trace": iters, "tail": r.stdout.splitlines()[-3:]}, f, indent=1)

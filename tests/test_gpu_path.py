@@ -135,7 +135,8 @@ def test_heightfield_lbvh_against_oracle(orc):
     scene = mi.Scene(desc)
     dev = scene.device()
     st = dev.bvh_stats
-    assert st["n_triangles"] == 2 * 199 * 199 + 12 and st["n_nodes"] == st["n_triangles"] - 1
+    assert st["n_triangles"] == 2 * 199 * 199 + 12
+    assert st["n_nodes"] == st["n_triangles"] - st["n_oversized"] - 1
     rng = np.random.default_rng(4)
     o = rng.uniform((-0.9, -0.8, -0.9), (0.9, 0.9, 0.9), size=(40000, 3)).astype(np.float32)
     d = rng.normal(size=(40000, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
@@ -157,6 +158,40 @@ def test_heightfield_lbvh_against_oracle(orc):
     assert fst["paths"] == rst["paths"] and abs(fst["segments"] - rst["segments"]) <= 2e-3 * rst["segments"]
     gi, ci = _image(film), _image(ref)
     assert _rel_mse(gi, ci) < 1e-3
+
+
+@pytest.mark.parametrize("knob", ["big_tris", "ray_sort"])
+def test_heightfield_build_and_scheduling_knobs_do_not_change_hits(orc, monkeypatch, knob):
+    """Two opt-in paths of the big-scene pipeline (both measured and left off by default, profiles/r02_summary.md) must
+    find the same hits: PRT_BIG_TRIS=1 keeps the 12 oversized box triangles out of the hierarchy (DScene::n_small) and tests
+    them one by one in every traversal (BVH2, BVH8, wavefront); PRT_WF_SORT=7 traces every bounce's rays in (origin cell,
+    octant) order through a permutation of the ray queue."""
+    if knob == "big_tris":
+        monkeypatch.setenv("PRT_BIG_TRIS", "1")
+    desc = scenes.heightfield_scene(200, (64, 36), 8)
+    scene = mi.Scene(desc)
+    dev = scene.device()
+    st = dev.bvh_stats
+    assert st["n_oversized"] == (12 if knob == "big_tris" else 0)
+    assert st["n_nodes"] == st["n_triangles"] - st["n_oversized"] - 1
+    rng = np.random.default_rng(5)
+    o = rng.uniform((-0.9, -0.8, -0.9), (0.9, 0.9, 0.9), size=(20000, 3)).astype(np.float32)
+    d = rng.normal(size=(20000, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(np.float32)
+    g = dev.trace_closest(o, d)
+    osc = orc.OracleScene(desc)
+    c = osc.trace_closest(o, d, prec=32)
+    assert (g["prim"] >= 0).all() and (g["prim"] == c["prim"]).mean() > 0.998
+    assert (~dev.trace_occluded(o, d, 1e-4)).all()
+    rp = scene.integrator().render_params(scene)
+    ref, rst = orc.render_path(osc, rp, seed=1, spp=8, prec=32)
+    for mode in ("wavefront", "mega"):
+        monkeypatch.setenv("PRT_PT_MODE", mode)
+        if knob == "ray_sort":
+            monkeypatch.setenv("PRT_WF_SORT", "7")
+        film, fst = dev.render_path(rp, seed=1, spp=8)
+        assert fst["paths"] == rst["paths"] and abs(fst["segments"] - rst["segments"]) <= 2e-3 * rst["segments"]
+        assert _rel_mse(_image(film), _image(ref)) < 1e-3
 
 
 def _render_mode(dev, rp, mode, monkeypatch, batch=None, **kw):
