@@ -80,6 +80,13 @@ int prt_scene_destroy(prt_scene *);
 int prt_scene_add_material(prt_scene *, int kind, const double p[8], const double emission_rgb[3], int *material_id);
 /* mi.traverse(scene)[...] = v ; params.update()  (USMain.py:259,264-265): no rebuild */
 int prt_scene_set_material_param(prt_scene *, int material_id, int index, double value);
+/* params['<shape>.to_world'] = T ; params.update(): moves one shape of a committed scene WITHOUT rebuilding it.  Analytic
+ * primitive: its 128-byte record is replaced.  Mesh: the shape's triangles are moved on the device (new * old^-1), the
+ * binary tree's boxes are refitted bottom-up over its unchanged topology and the 8-wide BVH is derived again -- no Morton
+ * codes, no sort, no hierarchy emission (the reference reaches the same point through
+ * mi.traverse(scene) / params.update(), USMain.py:259,264-265, where Mitsuba rebuilds its Embree scene).  Scenes of more
+ * than 2^22 triangles keep no topology and are rebuilt. */
+int prt_scene_set_shape_transform(prt_scene *, int shape_id, const double to_world[16]);
 int prt_scene_add_primitive(prt_scene *, int kind, const double to_world[16], int material_id, int flip_normals,
                             int *shape_id);
 /* v [nv][3], vn [nv][3] or NULL, idx [nt][3] (object space) */
@@ -100,6 +107,8 @@ typedef struct {
 } prt_bvh_stats;
 /* SoA upload + GPU LBVH build (Morton codes -> radix sort -> Karras hierarchy -> bottom-up refit) */
 int prt_scene_commit(prt_scene *, prt_bvh_stats *out /* nullable */);
+/* the statistics prt_scene_commit reported, as they stand now (a transform update refreshes build_ms / sah_cost / bounds) */
+int prt_scene_get_stats(prt_scene *, prt_bvh_stats *out);
 
 /* ---- ray queries == scene.ray_intersect(ray) (CustomIntegrator.py:146,159,309,324) ------------ */
 /* o,d [n][3] f32, tmax [n] or NULL (= inf).  Outputs nullable.  prim = -1, t = inf on a miss.

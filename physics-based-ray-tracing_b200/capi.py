@@ -27,7 +27,7 @@ QF_CONNECT_TO_TARGET = 1 << 4
 # every symbol include/prt_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "prt_last_error", "prt_version", "prt_device_count", "prt_create", "prt_destroy", "prt_device_info", "prt_profile_begin", "prt_profile_read", "prt_host_alloc", "prt_host_free",
-    "prt_scene_create", "prt_scene_destroy", "prt_scene_add_material", "prt_scene_set_material_param",
+    "prt_scene_create", "prt_scene_destroy", "prt_scene_add_material", "prt_scene_set_material_param", "prt_scene_set_shape_transform", "prt_scene_get_stats",
     "prt_scene_add_primitive", "prt_scene_add_mesh", "prt_scene_commit", "prt_trace_closest", "prt_trace_occluded",
     "prt_ultra_bsdf_sample", "prt_directivity_weights", "prt_acquire", "prt_acquire_dev", "prt_acquire_dev_angles", "prt_acquire_variants", "prt_acquire_trace", "prt_render_path",
     "prt_render_path_dev", "prt_render_image", "prt_film_develop_dev", "prt_das_beamform", "prt_envelope", "prt_us_render", "prt_pulse_shape", "prt_pulse_shape_dev",
@@ -137,6 +137,8 @@ def load():
     L.prt_scene_destroy.argtypes = [vp]
     L.prt_scene_add_material.argtypes = [vp, C.c_int, dp, dp, C.POINTER(C.c_int)]
     L.prt_scene_set_material_param.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+    L.prt_scene_set_shape_transform.argtypes = [vp, C.c_int, dp]
+    L.prt_scene_get_stats.argtypes = [vp, C.POINTER(BvhStatsC)]
     L.prt_scene_add_primitive.argtypes = [vp, C.c_int, dp, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.prt_scene_add_mesh.argtypes = [vp, dp, C.c_uint32, dp, u32p, C.c_uint32, dp, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.prt_scene_commit.argtypes = [vp, C.POINTER(BvhStatsC)]

@@ -300,6 +300,255 @@ __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const Acq
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Mesh scenes, per-lane state machine (PRT_ACQ_SM).
+//
+// k_acquire<true> runs a path segment as "closest-hit traversal, connection-ray traversal, shading" one after the other
+// inside one loop iteration.  Each of the two traversals is a while loop of its own: its lanes leave at different times and
+// the warp waits for the slowest (ncu r01 on the ring: the closest-hit loop runs 21 of 32 lanes, the any-hit loop 12).
+// Here a lane owns ONE ray query at a time -- the extend ray or the connection ray of its path -- and every loop iteration
+// advances every lane's query by a few nodes / one leaf, whichever kind of query it is: the traversal code, 85 % of the
+// kernel's instructions, is shared by all lanes at all times.  Lanes whose query is finished wait until PRT_ACQ_SM_BATCH of
+// them can be served together: `back` (deposit the echo of a finished connection ray, continue or end the path), `regen`
+// (start the next path), `front` (everything between the closest hit and the connection ray: receive element, UltraBSDF,
+// amplitude, time bin -- CustomIntegrator.py:153-224) -- the same arithmetic as segment<true>, split at the connection query.
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef PRT_ACQ_SM_DEFAULT
+#define PRT_ACQ_SM_DEFAULT 0
+#endif
+#ifndef PRT_ACQ_SM_BATCH
+#define PRT_ACQ_SM_BATCH 8
+#endif
+#ifndef PRT_ACQ_SM_NODES
+#define PRT_ACQ_SM_NODES 2                // inner-node steps per iteration before the leaf step
+#endif
+
+struct Echo {          // what the connection ray decides: deposit `value` into bin `flat` iff it is unoccluded
+    long long flat;    // < 0: out of range (nothing to deposit)
+    float value;
+    bool cont;         // the path goes on after this segment
+};
+
+// segment<true> from the closest hit to the connection ray (same statements, same order); returns the connection ray
+__device__ __forceinline__ void segment_front(const AcqDev &P, PathState &ps, const Hit &h, Echo &e, float3 &so, float3 &sec, float &vis_tmax) {
+    const float dist = h.t;
+    ps.geo += dist;                                                              // CI:209 / 315
+    const float tof_here = ps.tof + dist / P.c;                                  // CI:165 / 316
+    if (!(P.qf & PRT_QF_TOF_LAST_SEGMENT)) ps.tof = tof_here;
+    const float u_recv = ps.rng.next_f32();                                      // CI:153 / 319
+    const float s1 = ps.rng.next_f32();                                          // CI:173 / 337
+    const float s2 = ps.rng.next_f32();                                          // CI:174 / 337
+    const float u_rr = ps.rng.next_f32();                                        // CI:219 / 365
+    const int recv = min((int) floorf(u_recv * (float) P.n_e), P.n_e - 1);       // CI:154
+    const float3 tgt = xpoint(P.T0, P.T1, P.T2, mk3(elem_x(P, recv), 0.0f, 0.0f));   // CI:156-157
+    const float3 to_t = tgt - h.p;
+    const float dist_recv = sqrtf(dot(to_t, to_t));                              // CI:166 / 329
+    sec = mk3(to_t.x / dist_recv, to_t.y / dist_recv, to_t.z / dist_recv);       // CI:158 / 322
+    so = spawn_origin(h.p, h.ng, sec);
+    vis_tmax = PRT_INF;                                                          // Q1: maxt = inf
+    if (P.qf & PRT_QF_CONNECT_TO_TARGET) {
+        const float3 q = tgt - so;
+        vis_tmax = sqrtf(dot(q, q)) * (1.0f - 1e-4f);
+    }
+    ps.atten *= expf((P.att_k * dist) / 8.686f);                                 // CI:162-163 / 328
+    const float Ttot = (ps.t0 + tof_here) + dist_recv / P.c;                     // CI:167 / 329
+    const float phase = P.two_pi_f * Ttot;                                       // CI:168 / 330
+    const float3 md = -ps.d;
+    const float3 wi = mk3(dot(md, h.fs), dot(md, h.ft), dot(md, h.ns));          // si.wi
+    const DMaterial &mat = P.sc.mats[h.material];
+    float mZ = __ldg(&mat.p[0]), mA = __ldg(&mat.p[1]);                          // impedance, roughness (CB:12-18)
+    if ((P.var_mask >> (h.material & 63)) & 1ull) {                              // finite-difference variant (USMain.py:264)
+        if (P.var_index == 0) mZ = P.var_value;
+        else mA = P.var_value;
+    }
+    float3 dir; float pdf, a_resp; bool reflect;
+    ultra_bsdf_sample(wi, h.ng, h.ns, mZ, mA, s1, s2, dir, pdf, a_resp, reflect);   // CI:175 / 338
+    const float cos_theta = dot(h.ns, md);                                       // CI:176 / 340
+    ps.amp *= a_resp * cos_theta * fmaxf(pdf, 1e-6f);                            // CI:177 / 341
+    const float kf = rintf(Ttot * P.fs);                                         // CI:191 / 351-352 (half-even)
+    int k = (int) kf;
+    bool in_range = kf >= 0.0f && kf < (float) P.Tn;
+    if (P.qf & PRT_QF_CLAMP_TIDX) {                                              // CI:192
+        k = !(kf >= 0.0f) ? 0 : (kf > (float) (P.Tn - 1) ? P.Tn - 1 : k);
+        in_range = true;
+    }
+    const float w_i = directivity_wi(P.nT, sec, P.cos_m, P.cos_c, P.alpha_m, P.alpha_c);
+    const float w_o = dot(ps.d, h.ns) / P.n_rays;                                // CI:118,184
+    const float press = ps.atten * ps.amp * (w_i * w_o) * sinf(phase);           // CI:187 / 348
+    e.flat = in_range ? (long long) (((size_t) ps.a * P.n_e + recv) * (size_t) P.Tn + (size_t) k) : -1;   // CI:197-198
+    e.value = press * P.inv_spp;
+    ps.d = normalize(dir);                                                       // CI:205-206 / 358-359 (Q9)
+    ps.o = spawn_origin(h.p, h.ng, ps.d);
+    ps.depth++;                                                                  // CI:210 / 361
+    const float prod = ps.atten * ps.amp;
+    const float rr = (P.qf & PRT_QF_RR_NO_ABS) ? fminf(prod, 1.0f) : fminf(fabsf(prod), 1.0f);   // CI:220 / 364
+    const bool survive = u_rr < rr;                                              // CI:221
+    ps.atten = survive ? ps.atten / rr : 0.0f;                                   // CI:224
+    e.cont = !(P.qf & PRT_QF_SINGLE_BOUNCE) && survive && dot(ps.d, P.nT) >= P.cos_c &&      // CI:212-223 (Q11)
+             ps.depth < P.max_depth && ps.geo < P.max_len;                       // CI:141 / 307
+}
+
+template <bool GPRIMS>
+__global__ void __launch_bounds__(ACQ_THREADS, 3) k_acquire_sm(const AcqDev P) {
+    __shared__ DPrim sprims[MAX_SMEM_PRIMS];
+    const DPrim *prims = GPRIMS ? P.sc.prims : sprims;
+    if (!GPRIMS) {
+        const float4 *src = reinterpret_cast<const float4 *>(P.sc.prims);
+        float4 *dst = reinterpret_cast<float4 *>(sprims);
+        for (int i = threadIdx.x; i < P.sc.n_prims * (int) (sizeof(DPrim) / 16); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const DScene &sc = P.sc;
+    const uint32_t n_ae = (uint32_t) P.a_count * (uint32_t) P.n_e;
+    const uint32_t ae0 = (uint32_t) P.a_first * (uint32_t) P.n_e;
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    const uint64_t j0 = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t d_ae = (uint32_t) (stride % n_ae), d_si = (uint32_t) (stride / n_ae);
+    uint32_t ae = (uint32_t) (j0 % n_ae);
+    uint64_t si = j0 / n_ae;
+    if (P.tx && j0 < n_ae) {                      // transmit-delay table, CI:87-94 / 254-257
+        const uint32_t g = ae0 + (uint32_t) j0;
+        const float2 scv = __ldg(P.sincos + (int) (g / (uint32_t) P.n_e));
+        P.tx[g] = (elem_x(P, (int) (g % (uint32_t) P.n_e)) * scv.x) / P.c;
+    }
+    Counters cn = { 0, 0, 0, 0, 0 };
+    PathState ps;
+    Echo echo;
+    echo.flat = -1; echo.value = 0.0f; echo.cont = false;
+    // the lane's ray query
+    const int DONE = 0x7fffffff;
+    float3 qo = mk3(0, 0, 0), qinv = mk3(1, 1, 1);
+    RayPre rp;
+    rp.kx = 0; rp.ky = 1; rp.kz = 2; rp.Sx = rp.Sy = 0.0f; rp.Sz = 1.0f;
+    float tbest = 0.0f, b1 = 0.0f, b2 = 0.0f, prim_t = 0.0f;
+    int best = -1, best_prim = -1, ref = DONE, sp = 0;
+    int stack_ref[PRT_STACK];
+    float stack_t[PRT_STACK];
+    // 0: no path; 1: extend query running / finished; 2: connection query running / finished
+    int kind = 0;
+    bool exhausted = false;
+
+    // start a query on (o, d) within [0, tmax]: analytic primitives first (brute force), then the tree below that bound
+    auto begin_query = [&](float3 o, float3 d, float tmax, bool any) {
+        qo = o;
+        qinv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        rp = ray_precompute(d);
+        best = -1; best_prim = -1; sp = 0;
+        tbest = tmax;
+        bool blocked = false;
+        for (int i = 0; i < sc.n_prims; i++) {
+            const float t = intersect_prim(prims[i], o, d, tbest);
+            if (t >= 0.0f && (best_prim < 0 || t < tbest)) { best_prim = i; tbest = t; if (any) { blocked = true; break; } }
+        }
+        prim_t = tbest;
+        ref = (blocked || sc.n_small == 0) ? DONE : sc.root_ref;
+        cn.rays++;
+    };
+
+    for (;;) {
+        // ---------------- serve finished lanes, PRT_ACQ_SM_BATCH at a time ----------------
+        const bool ready = ref == DONE && !(kind == 0 && exhausted);
+        const unsigned mready = __ballot_sync(0xffffffffu, ready);
+        const unsigned mtrav = __ballot_sync(0xffffffffu, ref != DONE);
+        if (mready && (__popc(mready) >= PRT_ACQ_SM_BATCH || !mtrav)) {
+            if (ready && kind == 2) {                                     // back: the connection ray has decided
+                const bool visible = best < 0 && best_prim < 0;
+                if (visible && echo.flat >= 0) {
+                    if (P.buf) atomicAdd(P.buf + echo.flat, echo.value);  // CI:197-203 / 354
+                    cn.deposits++;
+                }
+                kind = echo.cont ? 1 : 0;
+                if (echo.cont) begin_query(ps.o, ps.d, PRT_INF, false);
+            } else if (ready && kind == 1) {                              // front: the extend ray has its closest hit
+                Hit h;
+                bool hit = true;
+                if (best >= 0 && (best_prim < 0 || tbest < prim_t)) fill_tri_hit(sc, best, tbest, b1, b2, h);
+                else if (best_prim >= 0) fill_prim_hit(prims[best_prim], best_prim, ps.o, ps.d, prim_t, h);
+                else hit = false;
+                if (!hit) {
+                    cn.misses++;                                          // CI:146-147 / 309-312
+                    kind = 0;
+                } else {
+                    cn.segments++;
+                    float3 so, sec;
+                    float vis_tmax;
+                    segment_front(P, ps, h, echo, so, sec, vis_tmax);
+                    kind = 2;
+                    begin_query(so, sec, vis_tmax, true);
+                }
+            }
+            if (ready && kind == 0 && ref == DONE) {                      // regen: next path of this lane
+                if (si < P.n_s) {
+                    init_path(P, ae0 + ae, P.s_offset + (uint32_t) si * P.s_stride, ps);
+                    ae += d_ae;
+                    si += d_si;
+                    if (ae >= n_ae) { ae -= n_ae; si++; }
+                    cn.paths++;
+                    if (P.max_depth > 0) {
+                        kind = 1;
+                        begin_query(ps.o, ps.d, PRT_INF, false);
+                    }
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, ref != DONE)) {
+            if (!__any_sync(0xffffffffu, ref == DONE && !(kind == 0 && exhausted))) break;
+            continue;
+        }
+        // ---------------- advance every running query: a few inner nodes, then one leaf ----------------
+#pragma unroll
+        for (int step = 0; step < PRT_ACQ_SM_NODES; step++) {
+            if ((unsigned) ref < (unsigned) DONE) {
+                const float4 *n = sc.nodes + 4 * (size_t) ref;
+                const float4 q0 = ldg4(n), q1 = ldg4(n + 1), q2 = ldg4(n + 2), q3 = ldg4(n + 3);
+                const float tl = box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, qo, qinv, tbest);
+                const float tr = box_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, qo, qinv, tbest);
+                const int rl = __float_as_int(q3.x), rr = __float_as_int(q3.y);
+                const bool hl = tl < PRT_INF, hr = tr < PRT_INF;
+                if (hl && hr) {
+                    const bool lf = tl <= tr;
+                    if (sp < PRT_STACK) { stack_ref[sp] = lf ? rr : rl; stack_t[sp] = lf ? tr : tl; sp++; }
+                    ref = lf ? rl : rr;
+                } else if (hl || hr) {
+                    ref = hl ? rl : rr;
+                } else {
+                    ref = DONE;
+                    while (sp > 0) { --sp; if (stack_t[sp] <= tbest) { ref = stack_ref[sp]; break; } }
+                }
+            }
+        }
+        if (ref < 0) {                                                    // a leaf: up to 4 triangles
+            const int code = ~ref;
+            const int first = code >> 2, count = (code & 3) + 1;
+            const RayRows rr = ray_rows(rp);
+            bool stop = false;
+            for (int j = 0; j < count; j++) {
+                const float4 *tv = sc.tri_v + 3 * (size_t) (first + j);
+                const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
+                if (intersect_tri_rows(rr, qo, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+                    best = first + j;
+                    if (kind == 2) { stop = true; break; }                // any hit
+                }
+            }
+            ref = DONE;
+            if (!stop)
+                while (sp > 0) { --sp; if (stack_t[sp] <= tbest) { ref = stack_ref[sp]; break; } }
+        }
+    }
+    if (P.stats) {
+        unsigned v[5] = { cn.paths, cn.segments, cn.rays, cn.deposits, cn.misses };
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            unsigned x = v[q];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) == 0 && x) atomicAdd(P.stats + q, (unsigned long long) x);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(ACQ_THREADS) k_acquire_trace(const AcqDev P, const uint64_t *__restrict__ path_idx, uint64_t n,
                                                                 prt_seg_record *rec) {
     __shared__ DPrim sprims[MAX_SMEM_PRIMS];
@@ -399,11 +648,15 @@ static int launch_acquire(prt_context *c, const AcqDev &P, cudaStream_t st) {
     const bool gp = P.sc.n_prims > MAX_SMEM_PRIMS;
     void (*kern)(const AcqDev) = tris ? (gp ? k_acquire<true, true> : k_acquire<true, false>)
                                       : (gp ? k_acquire<false, true> : k_acquire<false, false>);
+    // mesh scenes: the per-lane state machine (PRT_ACQ_SM=0 restores the segment-at-a-time kernel for A/B)
+    static const int use_sm = [] { const char *e = getenv("PRT_ACQ_SM"); return e && *e ? atoi(e) : PRT_ACQ_SM_DEFAULT; }();
+    const bool sm = tris && use_sm && P.sc.n_small == P.sc.n_tris;
+    if (sm) kern = gp ? k_acquire_sm<true> : k_acquire_sm<false>;
     PRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACQ_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     const uint64_t n_ae_l = (uint64_t) P.a_count * P.n_e;
     AcqDev Q = P;
-    Q.wae = (PRT_ACQ_WAE == 2 || (PRT_ACQ_WAE == 1 && tris)) && P.n_s >= 64;
+    Q.wae = !sm && (PRT_ACQ_WAE == 2 || (PRT_ACQ_WAE == 1 && tris)) && P.n_s >= 64;
     uint64_t want = ((Q.wae ? (P.n_s + 31) / 32 * 32 : P.n_s) * n_ae_l + ACQ_THREADS - 1) / ACQ_THREADS;
     uint64_t n_ae_blocks = (n_ae_l + ACQ_THREADS - 1) / ACQ_THREADS;
     if (want < n_ae_blocks) want = n_ae_blocks;  // the tx-delay table is written by the first n_a*n_e threads

@@ -411,8 +411,9 @@ struct BuildTemps {
 }  // namespace
 
 int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri_v_out, uint32_t *order_out,
-               float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t st, Bvh8Out *bvh8) {
+               float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t st, Bvh8Out *bvh8, LbvhTopology *keep) {
     (void) ctx;
+    if (keep) *keep = LbvhTopology();
     if (bvh8) *bvh8 = Bvh8Out{ nullptr, nullptr, nullptr, 0, 0, 0.0f };
     if (n == 0) {
         *root_ref = -1;
@@ -512,7 +513,55 @@ int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri
         stats->n_nodes = n >= 2 ? n - 1 : 0;
         stats->max_leaf_size = MAX_LEAF;
     }
-    return PRT_OK;      // ~BuildTemps releases every temporary
+    if (keep && n >= 2) {       // hand the topology over: take these six out of the temporaries' list
+        void *mine[6] = { children, ranges, parent_internal, parent_leaf, visit, root_box };
+        for (void *m : mine)
+            for (auto it = tmp.ptrs.begin(); it != tmp.ptrs.end(); ++it)
+                if (*it == m) { tmp.ptrs.erase(it); break; }
+        keep->children = children; keep->ranges = ranges; keep->parent_internal = parent_internal; keep->parent_leaf = parent_leaf;
+        keep->visit = visit; keep->root_box = root_box; keep->n = n;
+    }
+    return PRT_OK;      // ~BuildTemps releases every (other) temporary
+}
+
+void free_topology(LbvhTopology &t) {
+    cudaFree(t.children); cudaFree(t.ranges); cudaFree(t.parent_internal); cudaFree(t.parent_leaf); cudaFree(t.visit); cudaFree(t.root_box);
+    t = LbvhTopology();
+}
+
+int refit_lbvh(const LbvhTopology &t, const float4 *tri_v_sorted, float4 *nodes, prt_bvh_stats *stats, cudaStream_t st, Bvh8Out *bvh8) {
+    const uint32_t n = t.n;
+    if (bvh8) *bvh8 = Bvh8Out{ nullptr, nullptr, nullptr, 0, 0, 0.0f };
+    PRT_REQUIRE(n >= 2 && t.children, "refit_lbvh: no topology was kept for this scene");
+    BuildTemps tmp;
+    cudaEvent_t e0, e1;
+    PRT_CUDA(tmp.event(&e0));
+    PRT_CUDA(tmp.event(&e1));
+    const int T = 256;
+    const uint32_t nb = (n + T - 1) / T;
+    PRT_CUDA(cudaEventRecord(e0, st));
+    PRT_CUDA(cudaMemsetAsync(t.visit, 0, sizeof(int) * n, st));
+    PRT_CUDA(cudaMemsetAsync(t.root_box, 0, sizeof(float) * 8, st));
+    k_refit<<<nb, T, 0, st>>>(tri_v_sorted, (int) n, t.children, t.parent_internal, t.parent_leaf, (float *) nodes, t.visit, t.root_box);
+    k_emit<<<nb, T, 0, st>>>((int) n, t.children, t.ranges, (float *) nodes);
+    k_sah<<<nb, T, 0, st>>>((int) n, (const float *) nodes, t.ranges, t.parent_internal, t.root_box, t.root_box + 6);
+    PRT_CUDA(cudaGetLastError());
+    if (bvh8) {
+        int rc = build_bvh8(n, tri_v_sorted, (const float *) nodes, t.children, t.ranges, &bvh8->nodes8, &bvh8->n_nodes8, &bvh8->tri_v8,
+                            &bvh8->tri8_sorted, &bvh8->levels, st);
+        if (rc) return rc;
+    }
+    PRT_CUDA(cudaEventRecord(e1, st));
+    PRT_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        float ms = 0.0f, hb[8];
+        PRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        PRT_CUDA(cudaMemcpy(hb, t.root_box, sizeof(float) * 8, cudaMemcpyDeviceToHost));
+        stats->build_ms = ms;           // the refit's time replaces the build's
+        stats->sah_cost = hb[6];
+        for (int k = 0; k < 3; k++) { stats->scene_lo[k] = hb[k]; stats->scene_hi[k] = hb[3 + k]; }
+    }
+    return PRT_OK;
 }
 
 }  // namespace prt

@@ -51,6 +51,16 @@ struct HostMesh {
     bool has_n;
     int  shape, material, flip;
     uint32_t nt;
+    double to_world[16];    // the transform v / n were built with (prt_scene_set_shape_transform applies new * old^-1)
+};
+
+// what a refit-only update needs from the build: the binary tree's topology (prt_bvh.cu keeps it alive for scenes of up to
+// 2^22 triangles: 24 B per triangle)
+struct LbvhTopology {
+    int2 *children = nullptr, *ranges = nullptr;
+    int *parent_internal = nullptr, *parent_leaf = nullptr, *visit = nullptr;
+    float *root_box = nullptr;       // 8 floats (6 box + sah + pad)
+    uint32_t n = 0;
 };
 
 }  // namespace prt
@@ -125,6 +135,7 @@ struct prt_scene {
     float  *em_inv_area_dev;
     int     n_emitters;
     uint32_t n_tris, n_nodes;
+    prt::LbvhTopology topo;        // kept for prt_scene_set_shape_transform (empty: a transform change rebuilds)
     uint32_t n_small = 0;          // triangles in the hierarchy; the n_tris - n_small oversized ones sit behind them (DScene::n_small)
     int root_ref;
     uint64_t device_bytes;
@@ -145,8 +156,14 @@ struct Bvh8Out {
     float build_ms;
 };
 // bvh8 != nullptr: also derive the compressed 8-wide BVH from the binary tree (buffers owned by the caller afterwards)
+// keep != nullptr: the topology arrays are handed to the caller instead of being freed
 int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri_v_out, uint32_t *order_out,
-               float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t stream, Bvh8Out *bvh8 = nullptr);
+               float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t stream, Bvh8Out *bvh8 = nullptr,
+               LbvhTopology *keep = nullptr);
+// new boxes for an unchanged topology after the (sorted) vertices moved: bottom-up refit + padding / child refs, then the
+// 8-wide BVH is derived again from the refitted binary tree.  No Morton codes, no sort, no hierarchy emission.
+int refit_lbvh(const LbvhTopology &t, const float4 *tri_v_sorted, float4 *nodes, prt_bvh_stats *stats, cudaStream_t st, Bvh8Out *bvh8);
+void free_topology(LbvhTopology &t);
 int bvh8_annotate(uint32_t n, const uint32_t *tri8_sorted, const int4 *tri_info, const DMaterial *mats, float4 *tri_v8, cudaStream_t st);
 int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, const int2 *children, const int2 *ranges,
                float4 **out_nodes8, uint32_t *out_n_nodes8, float4 **out_tri_v8, uint32_t **out_tri8_sorted, int *out_levels,

@@ -256,6 +256,7 @@ int prt_scene_create(prt_context *c, prt_scene **out) {
 
 static void free_device(prt_scene *s) {
     cudaSetDevice(s->ctx->device);
+    free_topology(s->topo);
     if (s->prims_dev) cudaFree(s->prims_dev);
     if (s->mats_dev) cudaFree(s->mats_dev);
     if (s->nodes_dev) cudaFree(s->nodes_dev);
@@ -365,6 +366,7 @@ int prt_scene_add_mesh(prt_scene *s, const double *v, uint32_t nv, const double 
     hm.material = material_id;
     hm.flip = flip_normals ? 1 : 0;
     hm.nt = nt;
+    memcpy(hm.to_world, to_world, sizeof hm.to_world);
     hm.v.resize((size_t) nt * 9);
     if (vn) hm.n.resize((size_t) nt * 9);
     const double *m = to_world;
@@ -409,7 +411,80 @@ __global__ void k_gather_aux(const uint32_t *__restrict__ order, uint32_t n, con
 
 }  // extern "C"
 
+// area-emitter tables: emissive mesh shapes, uniform pick over emitters, area-weighted face pick (Mitsuba).  (Re)built from
+// the host meshes: at commit, and after a transform change of an emissive shape.
+static int build_emitters(prt_scene *s, size_t *bytes_out) {
+    if (s->em_tri_dev) cudaFree(s->em_tri_dev);
+    if (s->em_first_dev) cudaFree(s->em_first_dev);
+    if (s->shape_emitter_dev) cudaFree(s->shape_emitter_dev);
+    if (s->em_inv_area_dev) cudaFree(s->em_inv_area_dev);
+    s->em_tri_dev = nullptr;
+    s->em_first_dev = s->shape_emitter_dev = nullptr;
+    s->em_inv_area_dev = nullptr;
+    s->n_emitters = 0;
+        std::vector<float4> et;
+        std::vector<int> first, shape_em((size_t) s->n_shapes + 1, -1);
+        std::vector<float> inv_area;
+        for (auto &m : s->meshes) {
+            const DMaterial &mat = s->mats[m.material];
+            if (!(mat.emission[0] > 0 || mat.emission[1] > 0 || mat.emission[2] > 0) || m.nt == 0) continue;
+            shape_em[m.shape] = (int) inv_area.size();
+            first.push_back((int) (et.size() / 3));
+            double run = 0.0;
+            for (uint32_t t = 0; t < m.nt; t++) {
+                const float *v = &m.v[9 * (size_t) t];
+                double e0[3] = { (double) v[3] - v[0], (double) v[4] - v[1], (double) v[5] - v[2] };
+                double e1[3] = { (double) v[6] - v[0], (double) v[7] - v[1], (double) v[8] - v[2] };
+                double cx = e0[1] * e1[2] - e0[2] * e1[1], cy = e0[2] * e1[0] - e0[0] * e1[2], cz = e0[0] * e1[1] - e0[1] * e1[0];
+                run += 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+                et.push_back(make_float4(v[0], v[1], v[2], (float) run));
+                et.push_back(make_float4(v[3], v[4], v[5], __int_as_float_host(m.material)));
+                et.push_back(make_float4(v[6], v[7], v[8], m.flip ? 1.0f : 0.0f));
+            }
+            inv_area.push_back((float) (1.0 / run));
+        }
+        first.push_back((int) (et.size() / 3));
+        s->n_emitters = (int) inv_area.size();
+        PRT_CUDA(cudaMalloc(&s->shape_emitter_dev, sizeof(int) * shape_em.size()));
+        PRT_CUDA(cudaMemcpy(s->shape_emitter_dev, shape_em.data(), sizeof(int) * shape_em.size(), cudaMemcpyHostToDevice));
+        PRT_CUDA(cudaMalloc(&s->em_first_dev, sizeof(int) * first.size()));
+        PRT_CUDA(cudaMemcpy(s->em_first_dev, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice));
+        if (s->n_emitters) {
+            PRT_CUDA(cudaMalloc(&s->em_tri_dev, sizeof(float4) * et.size()));
+            PRT_CUDA(cudaMemcpy(s->em_tri_dev, et.data(), sizeof(float4) * et.size(), cudaMemcpyHostToDevice));
+            PRT_CUDA(cudaMalloc(&s->em_inv_area_dev, sizeof(float) * inv_area.size()));
+            PRT_CUDA(cudaMemcpy(s->em_inv_area_dev, inv_area.data(), sizeof(float) * inv_area.size(), cudaMemcpyHostToDevice));
+        }
+        *bytes_out = sizeof(float4) * et.size() + sizeof(int) * (first.size() + shape_em.size());
+    return PRT_OK;
+}
+
 namespace prt {
+struct XformDev { float D[12], Dinv[12]; };
+// moves the (sorted) triangles of one shape: vertices by D, corner normals by the inverse transpose; .w words are kept
+__global__ void k_xform_shape(uint32_t n, int shape, XformDev X, const int4 *__restrict__ info, float4 *tri_v, float4 *tri_n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || info[i].y != shape) return;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float4 v = tri_v[3 * (size_t) i + c];
+        const float x = v.x, y = v.y, z = v.z;
+        v.x = fmaf(X.D[0], x, fmaf(X.D[1], y, fmaf(X.D[2], z, X.D[3])));
+        v.y = fmaf(X.D[4], x, fmaf(X.D[5], y, fmaf(X.D[6], z, X.D[7])));
+        v.z = fmaf(X.D[8], x, fmaf(X.D[9], y, fmaf(X.D[10], z, X.D[11])));
+        tri_v[3 * (size_t) i + c] = v;
+        if (tri_n && (info[i].w & 1)) {
+            float4 q = tri_n[3 * (size_t) i + c];
+            const float a = q.x, b = q.y, d = q.z;
+            float wx = X.Dinv[0] * a + X.Dinv[4] * b + X.Dinv[8] * d, wy = X.Dinv[1] * a + X.Dinv[5] * b + X.Dinv[9] * d,
+                  wz = X.Dinv[2] * a + X.Dinv[6] * b + X.Dinv[10] * d;
+            const float l = sqrtf(wx * wx + wy * wy + wz * wz);
+            if (l > 0.0f) { q.x = wx / l; q.y = wy / l; q.z = wz / l; }
+            tri_n[3 * (size_t) i + c] = q;
+        }
+    }
+}
+
 // oversized triangles (DScene::n_small): v1.w = bits((sorted index << 2) | shading queue), as k_bvh8_annotate stamps the BVH8 copies
 __global__ void k_annotate_big(uint32_t first, uint32_t end, const int4 *__restrict__ tri_info, const DMaterial *__restrict__ mats,
                                float4 *__restrict__ tri_v) {
@@ -545,7 +620,9 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
         PRT_CUDA(cudaMalloc(&s->nodes_dev, sizeof(float4) * 4 * (nt > 1 ? nt - 1 : 1)));
         bytes += sizeof(float4) * 3 * nt + sizeof(int4) * nt + sizeof(float4) * 4 * (nt > 1 ? nt - 1 : 1);
         Bvh8Out b8;
-        int rc = build_lbvh(s->ctx, v_in, (uint32_t) n_small, s->tri_v_dev, order, s->nodes_dev, &s->root_ref, &s->stats, st, &b8);
+        // scenes of up to 2^22 triangles keep the tree's topology (24 B per triangle) so that a transform change can refit
+        int rc = build_lbvh(s->ctx, v_in, (uint32_t) n_small, s->tri_v_dev, order, s->nodes_dev, &s->root_ref, &s->stats, st, &b8,
+                            n_small <= (1u << 22) ? &s->topo : nullptr);
         if (rc) return rc;
         if (n_big) {       // the oversized triangles keep their staging order behind the sorted ones; k_gather_tris's stamp (v0.w = source index)
             std::vector<uint32_t> tail(n_big);
@@ -583,42 +660,11 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
         if (n_in) cudaFree(n_in);
         s->n_nodes = s->stats.n_nodes;
     }
-    // area-emitter tables: emissive mesh shapes, uniform pick over emitters, area-weighted face pick (Mitsuba)
     {
-        std::vector<float4> et;
-        std::vector<int> first, shape_em((size_t) s->n_shapes + 1, -1);
-        std::vector<float> inv_area;
-        for (auto &m : s->meshes) {
-            const DMaterial &mat = s->mats[m.material];
-            if (!(mat.emission[0] > 0 || mat.emission[1] > 0 || mat.emission[2] > 0) || m.nt == 0) continue;
-            shape_em[m.shape] = (int) inv_area.size();
-            first.push_back((int) (et.size() / 3));
-            double run = 0.0;
-            for (uint32_t t = 0; t < m.nt; t++) {
-                const float *v = &m.v[9 * (size_t) t];
-                double e0[3] = { (double) v[3] - v[0], (double) v[4] - v[1], (double) v[5] - v[2] };
-                double e1[3] = { (double) v[6] - v[0], (double) v[7] - v[1], (double) v[8] - v[2] };
-                double cx = e0[1] * e1[2] - e0[2] * e1[1], cy = e0[2] * e1[0] - e0[0] * e1[2], cz = e0[0] * e1[1] - e0[1] * e1[0];
-                run += 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
-                et.push_back(make_float4(v[0], v[1], v[2], (float) run));
-                et.push_back(make_float4(v[3], v[4], v[5], __int_as_float_host(m.material)));
-                et.push_back(make_float4(v[6], v[7], v[8], m.flip ? 1.0f : 0.0f));
-            }
-            inv_area.push_back((float) (1.0 / run));
-        }
-        first.push_back((int) (et.size() / 3));
-        s->n_emitters = (int) inv_area.size();
-        PRT_CUDA(cudaMalloc(&s->shape_emitter_dev, sizeof(int) * shape_em.size()));
-        PRT_CUDA(cudaMemcpy(s->shape_emitter_dev, shape_em.data(), sizeof(int) * shape_em.size(), cudaMemcpyHostToDevice));
-        PRT_CUDA(cudaMalloc(&s->em_first_dev, sizeof(int) * first.size()));
-        PRT_CUDA(cudaMemcpy(s->em_first_dev, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice));
-        if (s->n_emitters) {
-            PRT_CUDA(cudaMalloc(&s->em_tri_dev, sizeof(float4) * et.size()));
-            PRT_CUDA(cudaMemcpy(s->em_tri_dev, et.data(), sizeof(float4) * et.size(), cudaMemcpyHostToDevice));
-            PRT_CUDA(cudaMalloc(&s->em_inv_area_dev, sizeof(float) * inv_area.size()));
-            PRT_CUDA(cudaMemcpy(s->em_inv_area_dev, inv_area.data(), sizeof(float) * inv_area.size(), cudaMemcpyHostToDevice));
-        }
-        bytes += sizeof(float4) * et.size() + sizeof(int) * (first.size() + shape_em.size());
+        size_t eb = 0;
+        int rc = build_emitters(s, &eb);
+        if (rc) return rc;
+        bytes += eb;
     }
     s->device_bytes = bytes;
     s->stats.n_primitives = (uint32_t) s->prims.size();
@@ -630,6 +676,121 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
     s->stats.n_oversized = s->n_tris - s->n_small;
     s->committed = true;
     if (out) *out = s->stats;
+    return PRT_OK;
+}
+
+int prt_scene_set_shape_transform(prt_scene *s, int shape_id, const double to_world[16]) {
+    PRT_REQUIRE(s && to_world, "prt_scene_set_shape_transform: null argument");
+    PRT_REQUIRE(shape_id >= 0 && shape_id < s->n_shapes, "prt_scene_set_shape_transform: unknown shape");
+    double inv_new[12];
+    PRT_REQUIRE(invert_affine(to_world, inv_new), "prt_scene_set_shape_transform: singular to_world");
+    std::unique_lock<std::mutex> lk(s->ctx->mtx);
+    PRT_CUDA(cudaSetDevice(s->ctx->device));
+    for (size_t i = 0; i < s->prims.size(); i++) {
+        if (s->prims[i].shape != shape_id) continue;
+        // analytic primitive: new rows, one 128-byte upload; no hierarchy involved
+        DPrim &p = s->prims[i];
+        const int kind = p.kind, material = p.material, flip = p.flip;
+        const double *m = to_world;
+        p.w0 = make_float4((float) m[0], (float) m[1], (float) m[2], (float) m[3]);
+        p.w1 = make_float4((float) m[4], (float) m[5], (float) m[6], (float) m[7]);
+        p.w2 = make_float4((float) m[8], (float) m[9], (float) m[10], (float) m[11]);
+        p.o0 = make_float4((float) inv_new[0], (float) inv_new[1], (float) inv_new[2], (float) inv_new[3]);
+        p.o1 = make_float4((float) inv_new[4], (float) inv_new[5], (float) inv_new[6], (float) inv_new[7]);
+        p.o2 = make_float4((float) inv_new[8], (float) inv_new[9], (float) inv_new[10], (float) inv_new[11]);
+        if (kind == PRT_SPHERE) {
+            double r = std::sqrt(m[0] * m[0] + m[4] * m[4] + m[8] * m[8]);
+            p.aux = make_float4((float) m[3], (float) m[7], (float) m[11], (float) r);
+        } else {
+            float nx = (float) inv_new[8], ny = (float) inv_new[9], nz = (float) inv_new[10];
+            float l = std::sqrt(nx * nx + ny * ny + nz * nz);
+            p.aux = make_float4(nx / l, ny / l, nz / l, 0.0f);
+        }
+        p.kind = kind; p.material = material; p.flip = flip; p.shape = shape_id;
+        if (s->committed && s->prims_dev)
+            PRT_CUDA(cudaMemcpy(s->prims_dev + i, &p, sizeof(DPrim), cudaMemcpyHostToDevice));
+        return PRT_OK;
+    }
+    for (auto &hm : s->meshes) {
+        if (hm.shape != shape_id) continue;
+        // delta = new * old^-1 moves the world-space vertices the scene holds (host copy and device copy alike)
+        double inv_old[12];
+        PRT_REQUIRE(invert_affine(hm.to_world, inv_old), "prt_scene_set_shape_transform: singular previous transform");
+        double D[12];
+        for (int r = 0; r < 3; r++) {
+            for (int c = 0; c < 3; c++)
+                D[4 * r + c] = to_world[4 * r] * inv_old[c] + to_world[4 * r + 1] * inv_old[4 + c] + to_world[4 * r + 2] * inv_old[8 + c];
+            D[4 * r + 3] = to_world[4 * r] * inv_old[3] + to_world[4 * r + 1] * inv_old[7] + to_world[4 * r + 2] * inv_old[11] + to_world[4 * r + 3];
+        }
+        double D16[16] = { D[0], D[1], D[2], D[3], D[4], D[5], D[6], D[7], D[8], D[9], D[10], D[11], 0, 0, 0, 1 }, Dinv[12];
+        PRT_REQUIRE(invert_affine(D16, Dinv), "prt_scene_set_shape_transform: singular delta");
+        for (size_t k = 0; k < (size_t) hm.nt * 3; k++) {
+            float *v = &hm.v[3 * k];
+            const double x = v[0], y = v[1], z = v[2];
+            for (int r = 0; r < 3; r++) v[r] = (float) (D[4 * r] * x + D[4 * r + 1] * y + D[4 * r + 2] * z + D[4 * r + 3]);
+            if (hm.has_n) {
+                float *nn = &hm.n[3 * k];
+                const double a = nn[0], b = nn[1], c = nn[2];
+                double w[3];
+                for (int r = 0; r < 3; r++) w[r] = Dinv[r] * a + Dinv[4 + r] * b + Dinv[8 + r] * c;
+                const double l = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+                for (int r = 0; r < 3; r++) nn[r] = l > 0 ? (float) (w[r] / l) : 0.0f;
+            }
+        }
+        memcpy(hm.to_world, to_world, sizeof hm.to_world);
+        if (!s->committed) return PRT_OK;
+        if (!s->topo.children || s->n_small < 2) {      // no topology kept (> 2^22 triangles): full rebuild
+            s->committed = false;
+            lk.unlock();
+            return prt_scene_commit(s, nullptr);
+        }
+        cudaStream_t st = s->ctx->stream;
+        XformDev X;
+        for (int k = 0; k < 12; k++) { X.D[k] = (float) D[k]; X.Dinv[k] = (float) Dinv[k]; }
+        k_xform_shape<<<(s->n_tris + 255) / 256, 256, 0, st>>>(s->n_tris, shape_id, X, s->tri_info_dev, s->tri_v_dev, s->tri_n_dev);
+        PRT_CUDA(cudaGetLastError());
+        if (s->nodes8_dev) cudaFree(s->nodes8_dev);
+        if (s->tri_v8_dev) cudaFree(s->tri_v8_dev);
+        if (s->tri8_sorted_dev) cudaFree(s->tri8_sorted_dev);
+        s->nodes8_dev = s->tri_v8_dev = nullptr;
+        s->tri8_sorted_dev = nullptr;
+        Bvh8Out b8;
+        prt_bvh_stats rs = s->stats;
+        int rc = refit_lbvh(s->topo, s->tri_v_dev, s->nodes_dev, &rs, st, &b8);
+        if (rc) { s->committed = false; return rc; }
+        s->nodes8_dev = b8.nodes8; s->tri_v8_dev = b8.tri_v8; s->tri8_sorted_dev = b8.tri8_sorted;
+        s->n_nodes8 = b8.n_nodes8; s->bvh8_levels = b8.levels;
+        rc = bvh8_annotate(s->n_small, s->tri8_sorted_dev, s->tri_info_dev, s->mats_dev, s->tri_v8_dev, st);
+        if (rc) return rc;
+        s->stats.build_ms = rs.build_ms;
+        s->stats.sah_cost = rs.sah_cost;
+        s->stats.n_nodes8 = s->n_nodes8;
+        s->stats.bvh8_levels = (uint32_t) s->bvh8_levels;
+        {   // bounds of everything, oversized triangles included: from the host copies
+            float lo[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, hi[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
+            for (auto &m2 : s->meshes)
+                for (size_t k = 0; k < (size_t) m2.nt * 3; k++)
+                    for (int r = 0; r < 3; r++) { lo[r] = std::min(lo[r], m2.v[3 * k + r]); hi[r] = std::max(hi[r], m2.v[3 * k + r]); }
+            for (int r = 0; r < 3; r++) { s->stats.scene_lo[r] = lo[r]; s->stats.scene_hi[r] = hi[r]; }
+        }
+        const DMaterial &mat = s->mats[hm.material];
+        if (mat.emission[0] > 0 || mat.emission[1] > 0 || mat.emission[2] > 0) {
+            size_t eb = 0;
+            rc = build_emitters(s, &eb);
+            if (rc) return rc;
+        }
+        PRT_CUDA(cudaStreamSynchronize(st));
+        return PRT_OK;
+    }
+    set_error("prt_scene_set_shape_transform: shape not found");
+    return PRT_ERR_INVALID;
+}
+
+int prt_scene_get_stats(prt_scene *s, prt_bvh_stats *out) {
+    PRT_REQUIRE(s && out, "prt_scene_get_stats: null argument");
+    if (!s->committed) { set_error("prt_scene_get_stats: scene not committed"); return PRT_ERR_STATE; }
+    std::lock_guard<std::mutex> lk(s->ctx->mtx);
+    *out = s->stats;
     return PRT_OK;
 }
 

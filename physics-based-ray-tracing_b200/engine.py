@@ -129,6 +129,15 @@ class DeviceScene:
     def set_material_param(self, material: int, index: int, value: float):
         check(self.L.prt_scene_set_material_param(self.h, material, index, float(value)), "prt_scene_set_material_param")
 
+    def set_shape_transform(self, shape_index: int, to_world):
+        """Move one shape of the committed scene (refit, no rebuild: prt_scene_set_shape_transform); refreshes bvh_stats."""
+        m = np.ascontiguousarray(getattr(to_world, "matrix", to_world), dtype=np.float64).reshape(16)
+        check(self.L.prt_scene_set_shape_transform(self.h, int(shape_index), dptr(m)), "prt_scene_set_shape_transform")
+        self.desc.shapes[shape_index].to_world = m.reshape(4, 4).copy()
+        st = capi.BvhStatsC()
+        check(self.L.prt_scene_get_stats(self.h, C.byref(st)), "prt_scene_get_stats")
+        self.bvh_stats = st.as_dict()
+
     # -- scene.ray_intersect ----------------------------------------------------------------------
     def trace_closest(self, o, d, tmax=None):
         o = np.ascontiguousarray(o, dtype=np.float32).reshape(-1, 3)
@@ -203,10 +212,11 @@ class DeviceScene:
 
     def acquire_dev(self, params: AcqParams, buf_ptr: int, tx_ptr: int = 0, stats_ptr: int = 0, stream: int = 0,
                     seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1, angle_first: int = 0,
-                    angle_count: Optional[int] = None):
+                    angle_count: Optional[int] = None, ps=None):
         """Device-buffer entry point (accumulates into ``buf_ptr`` on ``stream``, asynchronous); optionally only the
-        steering angles [angle_first, angle_first + angle_count)."""
-        ps = capi.make_acq_params(params)
+        steering angles [angle_first, angle_first + angle_count).  ``ps``: a prebuilt capi.make_acq_params(params)."""
+        if ps is None:
+            ps = capi.make_acq_params(params)
         n = params.n_angles - angle_first if angle_count is None else angle_count
         check(self.L.prt_acquire_dev_angles(self.h, C.byref(ps), seed, spp, sample_offset, sample_stride, angle_first, n,
                                             C.c_void_p(buf_ptr), C.c_void_p(tx_ptr or None), C.c_void_p(stats_ptr or None),

@@ -526,12 +526,17 @@ class SceneParameters(dict):
                     alias.setdefault(f"shape.bsdf.{pname}", []).append((sh.material, pi))
         for k, v in alias.items():
             self._targets[k] = v
+        self._shape_keys = {}
+        for si, sh in enumerate(scene.desc.shapes):
+            key = f"{sh.id}.to_world"
+            dict.__setitem__(self, key, Transform4f(sh.to_world))
+            self._shape_keys[key] = si
         integ = scene.integrator()
         if integ is not None and hasattr(integ, "pitch"):
             dict.__setitem__(self, "integrator.pitch", integ.pitch)
 
     def __setitem__(self, key, value):
-        if key not in self._targets and key != "integrator.pitch":
+        if key not in self._targets and key != "integrator.pitch" and key not in self._shape_keys:
             raise KeyError(key)
         dict.__setitem__(self, key, value)
         self._dirty.add(key)
@@ -548,6 +553,14 @@ class SceneParameters(dict):
             val = dict.__getitem__(self, key)
             if key == "integrator.pitch":
                 self._scene.integrator().pitch = float(val)
+                continue
+            if key in self._shape_keys:        # '<shape id>.to_world': refit-only update of the device scene
+                si = self._shape_keys[key]
+                m = np.array(getattr(val, "matrix", val), dtype=np.float64).reshape(4, 4)
+                if self._scene._device_scene is not None:
+                    self._scene._device_scene.set_shape_transform(si, m)
+                else:
+                    self._scene.desc.shapes[si].to_world = m
                 continue
             v = float(np.asarray(val.numpy() if hasattr(val, "numpy") else val).reshape(-1)[0])
             for material, index in self._targets[key]:

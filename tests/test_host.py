@@ -176,6 +176,22 @@ def test_reference_scripts_run_unchanged_up_to_the_gpu_boundary():
     assert "ModuleNotFoundError" not in r.stderr and "KeyError" not in r.stderr and "AttributeError" not in r.stderr
 
 
+def test_packed_statistics_survive_a_float32_sum():
+    """distributed.acquire_sharded sums its u64 path counters inside the float32 all-reduce of the channel buffer: packed as
+    20-bit words they must come back exact for up to 16 ranks."""
+    import torch
+    from prt_b200.distributed import pack_stats, unpack_stats
+    g = torch.Generator().manual_seed(1)
+    ranks = [torch.randint(0, 2 ** 62, (8,), generator=g, dtype=torch.int64) for _ in range(16)]
+    ranks[3][0] = 2 ** 62 - 1
+    ranks[5][1] = 0
+    acc = torch.zeros(8, 4, dtype=torch.float32)
+    for r in ranks:
+        acc += pack_stats(r)                          # what the float32 sum all-reduce computes
+    want = [sum(int(r[i]) for r in ranks) for i in range(8)]
+    assert unpack_stats(acc.numpy()) == want
+
+
 def test_mesh_readers_roundtrip(tmp_path):
     from prt_b200.meshio import load_obj, load_ply
     p = tmp_path / "q.obj"
@@ -285,7 +301,7 @@ class _Stream: cuda_stream = 0
 class _FakeScene:
     def __init__(self, buf): self.buf, self.calls = buf, []
     def acquire_dev(self, params, buf_ptr, tx_ptr, stats_ptr, stream, seed=0, spp=1, sample_offset=0, sample_stride=1,
-                    angle_first=0, angle_count=None):
+                    angle_first=0, angle_count=None, ps=None):
         self.calls.append((angle_first, angle_count, sample_offset, sample_stride))
         self.buf[angle_first] += float(10 * (rank + 1) + angle_first)
 pbuf = torch.zeros(5, 7)
@@ -294,6 +310,15 @@ acquire_allreduce_pipelined(fake, _Params(), pbuf, torch.zeros(1), torch.zeros(1
 assert fake.calls == [(a, 1, rank, 2) for a in range(5)], fake.calls
 for a in range(5):
     assert torch.equal(pbuf[a], torch.full((7,), float(10 + 20 + 2 * a))), (a, pbuf[a])
+# acquire_sharded's layout: the path counters ride as 32 float words right behind the LAST angle slice, in ITS all-reduce
+from prt_b200.distributed import pack_stats, unpack_stats
+flat = torch.zeros(5 * 7 + 32)
+flat[4 * 7:5 * 7] = float(rank + 1)
+mine = torch.tensor([2 ** 40 + rank, 3, 5 * (rank + 1), 0, 2 ** 33 * (rank + 1), 0, 0, 1], dtype=torch.int64)
+flat[5 * 7:].view(8, 4).copy_(pack_stats(mine))
+dist.all_reduce(flat[4 * 7:], op=dist.ReduceOp.SUM)
+assert torch.equal(flat[4 * 7:5 * 7], torch.full((7,), 3.0))
+assert unpack_stats(flat[5 * 7:].numpy()) == [2 ** 41 + 1, 6, 15, 0, 3 * 2 ** 33, 0, 0, 2]
 dist.destroy_process_group()
 print("ok", rank)
 '''
