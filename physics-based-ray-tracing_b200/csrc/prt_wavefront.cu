@@ -249,6 +249,9 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_generate(const PtDev P,
 // ------------------------------------------------------------------------------------------------------------------
 // ray queries with dynamic fetch over the compressed 8-wide BVH
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef WF_TRI_PEEL
+#define WF_TRI_PEEL 0                    // per-lane triangle rounds only while > WF_COOP_MAX lanes have one; tails go to the cooperative test
+#endif
 #ifndef WF_TOPN
 #define WF_TOPN 0                         // first WF_TOPN nodes of the 8-wide BVH (breadth-first: 73 = top three levels) staged in shared memory
 #endif
@@ -509,7 +512,37 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
 #endif
         }
         // ---- the triangles those nodes yielded ----
-        const unsigned mT = __ballot_sync(FULL, tg.y != 0u);
+        unsigned mT = __ballot_sync(FULL, tg.y != 0u);
+#if WF_TRI_PEEL
+        if (__popc(mT) > WF_COOP_MAX) {
+            // most lanes hold triangles (small scenes, coherent rays): every lane tests ONE triangle of its own list per round,
+            // for as long as more than WF_COOP_MAX lanes still have one.  The lists differ in length (0 .. 24): running them
+            // to exhaustion left 6.7 of 32 lanes active on average (ncu r01, height field), so the long tails are handed to the
+            // cooperative branch below, which deals (ray, triangle) pairs out evenly.  The shear rows of the selection-free
+            // triangle test are rebuilt here rather than carried through the traversal loop (nine more live registers spill).
+#if PRT_TRI_ROWS
+            const RayRows rr = ray_rows(rp);
+#endif
+            do {
+                if (tg.y) {
+                    const int bit = 31 - __clz(tg.y);
+                    tg.y &= ~(1u << bit);
+                    const float4 *tv = sc.tri_v8 + 3 * (size_t) (tg.x + (uint32_t) bit);
+                    const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
+#if PRT_TRI_ROWS
+                    if (intersect_tri_rows(rr, r8.o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#else
+                    if (intersect_tri_wt(rp, r8.o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
+#endif
+                        best = __float_as_int(b.w);
+                        if (ANY) { busy = false; tg.y = 0u; }
+                    }
+                }
+                mT = __ballot_sync(FULL, tg.y != 0u);
+            } while (__popc(mT) > WF_COOP_MAX);
+        }
+        if (mT) {
+#else
         if (__popc(mT) > WF_COOP_MAX) {
             // most lanes hold triangles (small scenes, coherent rays): every lane walks its own list.  The shear rows of
             // the selection-free triangle test (intersect_tri_rows) are rebuilt here, once per list, rather than carried
@@ -533,6 +566,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                 }
             }
         } else if (mT) {
+#endif
             // A few lanes hold several triangles each and most hold none (the per-lane loop ran with 4.5 of 32 lanes
             // on incoherent rays).  The warp's (ray, triangle) pairs are numbered by a prefix sum and dealt out one
             // per lane: a lane pulls the owning ray through shuffles, tests its triangle, and the closest hit per

@@ -3,7 +3,7 @@
 #   usage: tools/make_profiles.sh <tag of gpu_ncu_full.sh> <round prefix, e.g. r01>
 TAG=$1; R=${2:-r01}
 cd "$(dirname "$0")/.."
-for r in hf_closest hf_shadow hf_shade cbox_closest cbox_shade sphere_box ring; do
+for r in ${REPS:-hf_closest hf_shadow hf_shade cbox_closest cbox_shade sphere_box ring}; do
   rep=gpurun_out/prof_${TAG}_$r.ncu-rep
   [ -f $rep ] || { echo "missing $rep"; continue; }
   python tools/ncu_regions.py $rep 40 > profiles/${R}_ncu_$r.txt 2>&1
