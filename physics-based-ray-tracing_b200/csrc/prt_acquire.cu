@@ -65,13 +65,70 @@ __device__ __forceinline__ void init_path(const AcqDev &P, uint32_t ae, uint32_t
     ps.rng = path_rng(P.seed, (uint64_t) ae * (uint64_t) P.spp_total + (uint64_t) s);      // RNG contract, SURVEY.md 8(d)
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Echo cache: software combining of deposits in shared memory.
+//
+// The reference's primary ray depends on (angle, element) only (CustomIntegrator.py:270-273), so all 209 716 samples of a pair
+// hit the same point, and its first-segment echo can only land in 64 bins (one per receive element).  One launch therefore
+// fires 13.4 M `red.global.add.f32` at a few thousand addresses -- or at a few HUNDRED, for the steered angles whose
+// transmit delays line the elements' echoes up in the same time bin: the +-15 degree launches of the headline workload took
+// 2.05 ms against 1.06 ms at 0 degrees for the same number of rays (profiles/r02_launches_bench.csv), the L2 serialising
+// same-address atomics.  Each CTA keeps a direct-mapped table of (bin, partial sum) in shared memory: a deposit whose bin
+// owns its slot is a shared-memory atomic; a bin that finds its slot taken by another goes to global memory as before; the
+// table is flushed with one global atomic per occupied slot when the CTA retires.  Sums are re-associated (atomics never
+// had an order), nothing else changes.
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef PRT_ACQ_CACHE
+#define PRT_ACQ_CACHE 2048                // slots per CTA (power of two; 0 = deposits go straight to global memory)
+#endif
+// the mesh kernel's path stash already takes 35 KB of the 48 KB of static shared memory: it gets a quarter-size table
+#define ECHO_SLOTS(tris) ((tris) ? PRT_ACQ_CACHE / 4 : PRT_ACQ_CACHE)
+#define ECHO_BITS(tris) (__builtin_ctz(PRT_ACQ_CACHE) - ((tris) ? 2 : 0))
+struct EchoCache {
+    unsigned *key;    // [1 << bits] bin index, 0xffffffff = free
+    float *val;
+    int bits;
+};
+
+__device__ __forceinline__ void echo_add(const AcqDev &P, const EchoCache &ec, size_t flat, float v) {
+#if PRT_ACQ_CACHE
+    if (flat < 0xffffffffull) {
+        const unsigned a = (unsigned) flat;
+        const unsigned h = (a * 2654435761u) >> (32 - ec.bits);
+        unsigned k = ec.key[h];
+        if (k == 0xffffffffu) k = atomicCAS(&ec.key[h], 0xffffffffu, a), k = k == 0xffffffffu ? a : k;
+        if (k == a) { atomicAdd(&ec.val[h], v); return; }
+    }
+#endif
+    atomicAdd(P.buf + flat, v);
+}
+
+__device__ __forceinline__ void echo_cache_init(const EchoCache &ec) {
+#if PRT_ACQ_CACHE
+    for (int i = threadIdx.x; i < (1 << ec.bits); i += blockDim.x) { ec.key[i] = 0xffffffffu; ec.val[i] = 0.0f; }
+    __syncthreads();
+#endif
+}
+
+__device__ __forceinline__ void echo_cache_flush(const AcqDev &P, const EchoCache &ec) {
+#if PRT_ACQ_CACHE
+    __syncthreads();
+    for (int i = threadIdx.x; i < (1 << ec.bits); i += blockDim.x) {
+        const unsigned k = ec.key[i];
+        const float v = ec.val[i];
+        if (k != 0xffffffffu && v != 0.0f) atomicAdd(P.buf + k, v);
+    }
+#endif
+}
+
 struct Counters {
     unsigned paths, segments, rays, deposits, misses;
 };
 
 // executes ONE segment of the path; returns false when the path terminates.  rec != nullptr records decisions.
 template <bool TRIS>
-__device__ __forceinline__ bool segment(const AcqDev &P, const DPrim *prims, PathState &ps, Counters &cn, prt_seg_record *rec) {
+__device__ __forceinline__ bool segment(const AcqDev &P, const DPrim *prims, PathState &ps, Counters &cn, prt_seg_record *rec,
+                                        const EchoCache &ec) {
     Hit h;
     cn.rays++;
     if (!closest_hit<TRIS>(P.sc, prims, ps.o, ps.d, PRT_INF, h)) { cn.misses++; return false; }   // CI:146-147 / 309-312
@@ -133,7 +190,7 @@ __device__ __forceinline__ bool segment(const AcqDev &P, const DPrim *prims, Pat
         press = ps.atten * ps.amp * (w_i * w_o) * sinf(phase);                   // CI:187 / 348
     }
     if (deposit) {
-        if (P.buf) atomicAdd(P.buf + ((size_t) ps.a * P.n_e + recv) * (size_t) P.Tn + (size_t) k, press * P.inv_spp);   // CI:197-203 / 354
+        if (P.buf) echo_add(P, ec, ((size_t) ps.a * P.n_e + recv) * (size_t) P.Tn + (size_t) k, press * P.inv_spp);   // CI:197-203 / 354
         cn.deposits++;
     }
     ps.d = normalize(dir);                                                       // CI:205-206 / 358-359 (Q9)
@@ -183,6 +240,16 @@ static constexpr int ACQ_STASH_CAP = 64;  // < 32 parked before an iteration + a
 template <bool TRIS, bool GPRIMS>
 __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const AcqDev P) {
     __shared__ DPrim sprims[MAX_SMEM_PRIMS];
+    constexpr bool TRIS_K = TRIS;
+    EchoCache ec;
+#if PRT_ACQ_CACHE
+    __shared__ unsigned s_ec_key[ECHO_SLOTS(TRIS_K)];
+    __shared__ float s_ec_val[ECHO_SLOTS(TRIS_K)];
+    ec.key = s_ec_key; ec.val = s_ec_val; ec.bits = ECHO_BITS(TRIS_K);
+#else
+    ec.key = nullptr; ec.val = nullptr; ec.bits = 0;
+#endif
+    echo_cache_init(ec);
 #if PRT_ACQ_LDS
     const DPrim *prims = GPRIMS ? P.sc.prims : sprims;
     if (!GPRIMS) {
@@ -256,7 +323,7 @@ __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const Acq
                 cn.paths++;
                 have = P.max_depth > 0;
             }
-            const bool cont = have && segment<TRIS>(P, prims, ps, cn, nullptr);
+            const bool cont = have && segment<TRIS>(P, prims, ps, cn, nullptr, ec);
             const unsigned m = __ballot_sync(0xffffffffu, cont);
             if (cont) {
                 float *e = stash[n_st + __popc(m & ((1u << lane) - 1u))];
@@ -285,9 +352,10 @@ __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const Acq
                 live = P.max_depth > 0;
                 if (!live) continue;
             }
-            live = segment<TRIS>(P, prims, ps, cn, nullptr);
+            live = segment<TRIS>(P, prims, ps, cn, nullptr, ec);
         }
     }
+    if (P.buf) echo_cache_flush(P, ec);
     if (P.stats) {
         unsigned v[5] = { cn.paths, cn.segments, cn.rays, cn.deposits, cn.misses };
 #pragma unroll
@@ -391,6 +459,16 @@ __device__ __forceinline__ void segment_front(const AcqDev &P, PathState &ps, co
 template <bool GPRIMS>
 __global__ void __launch_bounds__(ACQ_THREADS, 3) k_acquire_sm(const AcqDev P) {
     __shared__ DPrim sprims[MAX_SMEM_PRIMS];
+    constexpr bool TRIS_K = false;           // no stash in this kernel: the full table fits
+    EchoCache ec;
+#if PRT_ACQ_CACHE
+    __shared__ unsigned s_ec_key[ECHO_SLOTS(TRIS_K)];
+    __shared__ float s_ec_val[ECHO_SLOTS(TRIS_K)];
+    ec.key = s_ec_key; ec.val = s_ec_val; ec.bits = ECHO_BITS(TRIS_K);
+#else
+    ec.key = nullptr; ec.val = nullptr; ec.bits = 0;
+#endif
+    echo_cache_init(ec);
     const DPrim *prims = GPRIMS ? P.sc.prims : sprims;
     if (!GPRIMS) {
         const float4 *src = reinterpret_cast<const float4 *>(P.sc.prims);
@@ -454,7 +532,7 @@ __global__ void __launch_bounds__(ACQ_THREADS, 3) k_acquire_sm(const AcqDev P) {
             if (ready && kind == 2) {                                     // back: the connection ray has decided
                 const bool visible = best < 0 && best_prim < 0;
                 if (visible && echo.flat >= 0) {
-                    if (P.buf) atomicAdd(P.buf + echo.flat, echo.value);  // CI:197-203 / 354
+                    if (P.buf) echo_add(P, ec, (size_t) echo.flat, echo.value);  // CI:197-203 / 354
                     cn.deposits++;
                 }
                 kind = echo.cont ? 1 : 0;
@@ -537,6 +615,7 @@ __global__ void __launch_bounds__(ACQ_THREADS, 3) k_acquire_sm(const AcqDev P) {
                 while (sp > 0) { --sp; if (stack_t[sp] <= tbest) { ref = stack_ref[sp]; break; } }
         }
     }
+    if (P.buf) echo_cache_flush(P, ec);
     if (P.stats) {
         unsigned v[5] = { cn.paths, cn.segments, cn.rays, cn.deposits, cn.misses };
 #pragma unroll
@@ -560,7 +639,9 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire_trace(const AcqDev P, c
     Counters cn = { 0, 0, 0, 0, 0 };
     init_path(P, (uint32_t) (path / P.spp_total), (uint32_t) (path % P.spp_total), ps);
     bool live = P.max_depth > 0;
-    while (live) live = segment<true>(P, prims, ps, cn, rec + i * (uint64_t) P.max_depth);
+    EchoCache ec;
+    ec.key = nullptr; ec.val = nullptr; ec.bits = 0;         // the decision trace deposits nothing (P.buf == nullptr)
+    while (live) live = segment<true>(P, prims, ps, cn, rec + i * (uint64_t) P.max_depth, ec);
 }
 
 static int fill_params(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t s_offset,

@@ -542,7 +542,7 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
                 hi[o] = make_int4((int) o, m.shape, m.material, (m.has_n ? 1 : 0) | (m.flip ? 2 : 0));
             }
         }
-        // Oversized triangles (bounding-box area > 1024 x the mean; at most 64, largest first) can be moved to the END of the
+        // Oversized triangles (bounding-box area > 1024 x the mean; at most 24, largest first) can be moved to the END of the
         // staging arrays and kept out of the hierarchy (DScene::n_small): PRT_BIG_TRIS=1.  OFF by default -- measured on
         // B200 (profiles/r02_summary.md): on the 10 M-triangle height field the tree gets 35 % cheaper by absolute SAH cost,
         // but the twelve brute-force tests run when a lane fetches its ray, i.e. with 2-4 active lanes per warp, and the
@@ -572,9 +572,9 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
             if (enabled)
                 for (uint64_t t = 0; t < nt; t++)
                     if (area[t] > limit) big.push_back(t);
-            if (big.size() > 64) {
-                std::partial_sort(big.begin(), big.begin() + 64, big.end(), [&](uint64_t a, uint64_t b) { return area[a] > area[b]; });
-                big.resize(64);
+            if (big.size() > 24) {       // the wavefront deals them out as ONE triangle group (24-bit mask)
+                std::partial_sort(big.begin(), big.begin() + 24, big.end(), [&](uint64_t a, uint64_t b) { return area[a] > area[b]; });
+                big.resize(24);
                 std::sort(big.begin(), big.end());
             }
             n_big = big.size();

@@ -249,9 +249,18 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_generate(const PtDev P,
 // ------------------------------------------------------------------------------------------------------------------
 // ray queries with dynamic fetch over the compressed 8-wide BVH
 // ------------------------------------------------------------------------------------------------------------------
+// triangle `off` of a group: base < 2^31 -> BVH8 leaf order (tri_v8); bit 31 set -> the oversized triangles in tri_v
+__device__ __forceinline__ const float4 *wf_tri_ptr(const DScene &sc, uint32_t base, uint32_t off) {
+    const float4 *arr = (base >> 31) ? sc.tri_v : sc.tri_v8;
+    return arr + 3 * (size_t) ((base & 0x7fffffffu) + off);
+}
+
 #ifndef WF_TRI_PEEL
 #define WF_TRI_PEEL 0                    // per-lane triangle rounds only while > WF_COOP_MAX lanes have one; tails go to the cooperative test
 #endif
+#ifndef WF_TRI_DEFER
+#define WF_TRI_DEFER 0                   // > 0: a lane keeps the triangles its node step yielded and waits; the warp tests them only in
+#endif                                    // full rounds of 32 (ray, triangle) pairs, or when no lane can advance otherwise
 #ifndef WF_TOPN
 #define WF_TOPN 0                         // first WF_TOPN nodes of the 8-wide BVH (breadth-first: 73 = top three levels) staged in shared memory
 #endif
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
     extern __shared__ float4 s_dyn[];
     DPrim *sprims = reinterpret_cast<DPrim *>(s_dyn);
     uint2 *sstack = reinterpret_cast<uint2 *>(s_dyn + (sc_n_smem_prims(P.sc) * (int) (sizeof(DPrim) / 16))) + threadIdx.x;
-    __shared__ int s_owner[WF_TRACE_THREADS], s_win[WF_TRACE_THREADS];
+    __shared__ int s_win[WF_TRACE_THREADS];
     __shared__ unsigned s_tmin[WF_TRACE_THREADS];
 #if WF_TOPN
     // The top levels are fetched by every ray of every warp.  They hit in L1 anyway (ncu r01: top of the tree is < 6 KB), so
@@ -297,12 +306,13 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
     int *head = C + (ANY ? C_HEAD_SH : C_HEAD_EXT);
     const WfRays R = ANY ? B.sh : B.ext[bounce & 1];
     const int lane = threadIdx.x & 31;
-    int *so = s_owner + (threadIdx.x & ~31), *sw = s_win + (threadIdx.x & ~31);
+    int *sw = s_win + (threadIdx.x & ~31);
     unsigned *stm = s_tmin + (threadIdx.x & ~31);
 
     int pool_next = 0, pool_end = 0;     // warp-uniform: queue positions this warp has reserved
     bool dry = false;                    // warp-uniform: the queue is exhausted
     bool has = false, busy = false;      // lane holds a ray / its traversal is still running
+    bool fresh = false;                  // the ray has not been tested against the oversized triangles yet
     uint32_t slot = 0, qpos = 0;         // path slot, queue position of the ray
     Bvh8Ray r8;
     r8.o = mk3(0, 0, 0); r8.inv = mk3(1, 1, 1); r8.octinv4 = 0;
@@ -313,6 +323,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
     float tbest = 0.0f, b1 = 0.0f, b2 = 0.0f, prim_t = 0.0f;
     int best = -1, best_prim = -1, sp = 0;      // best: (sorted triangle << 2) | shading queue, or -1
     uint2 ng = make_uint2(0, 0);                // node group in hand: child base, hit bits | imask
+    uint2 tg = make_uint2(0u, 0u);              // triangle group in hand: base, 24-bit mask (consumed by the triangle phase)
     uint2 gstack[BVH8_STACK > WF_SSTACK ? BVH8_STACK - WF_SSTACK : 1];
     unsigned n_rays = 0, n_valid = 0;
 
@@ -442,28 +453,13 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                         }
                         if (!ANY) tbest = prim_t;
                     }
-                    if (sc.n_small < sc.n_tris && !blocked) {
-                        // the scene's oversized triangles (DScene::n_small) are not in the hierarchy: test them here, one by
-                        // one; the traversal below then starts with their nearest hit as its bound
-#if PRT_TRI_ROWS
-                        const RayRows rr = ray_rows(rp);
-#endif
-                        for (int j = sc.n_small; j < sc.n_tris; j++) {
-                            const float4 *tv = sc.tri_v + 3 * (size_t) j;
-                            const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
-#if PRT_TRI_ROWS
-                            if (intersect_tri_rows(rr, r8.o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
-#else
-                            if (intersect_tri_wt(rp, r8.o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
-#endif
-                                best = __float_as_int(b.w);
-                                if (ANY) { blocked = true; break; }
-                            }
-                        }
-                    }
+                    // the scene's oversized triangles (DScene::n_small) are not in the hierarchy: they become this ray's FIRST
+                    // triangle group, dealt out with everybody else's leaf triangles in the triangle phase below (a loop at
+                    // this point would run with the 2-4 lanes that happen to refill together: measured 81 -> 108 ms)
+                    fresh = sc.n_small < sc.n_tris && !blocked;
                     sp = 0;
                     ng = make_uint2(0u, 0x80000000u);
-                    busy = !(sc.n_small == 0 || blocked);
+                    busy = !((sc.n_small == 0 && !fresh) || blocked);
                 }
                 pool_next += min(avail, __popc(need));
                 need = __ballot_sync(FULL, !has);
@@ -472,8 +468,21 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
         if (!__any_sync(FULL, has)) break;
 
         // ---- one wide node per lane and iteration ----
-        uint2 tg = make_uint2(0u, 0u);
-        if (busy && ng.y > 0x00ffffffu) {
+#if WF_TRI_DEFER
+        const bool can_step = busy && tg.y == 0u;      // a lane with untested triangles waits for the warp's next triangle round
+#else
+        const bool can_step = busy;
+        tg = make_uint2(0u, 0u);
+#endif
+        bool stepped = false;
+        if (can_step && fresh) {
+            stepped = true;
+            // bit 31 of the base: the group lives in tri_v (sorted order, behind the n_small triangles of the tree), not in tri_v8
+            tg = make_uint2(0x80000000u | (uint32_t) sc.n_small, (1u << (sc.n_tris - sc.n_small)) - 1u);
+            fresh = false;
+            if (sc.n_small == 0) ng.y = 0u;                  // no tree at all: the traversal ends after this group
+        } else if (can_step && ng.y > 0x00ffffffu) {
+            stepped = true;
             const uint32_t hits = ng.y, imask8 = ng.y & 0xffu;
             const int bit = 31 - __clz(hits);
             ng.y &= ~(1u << bit);
@@ -527,7 +536,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                 if (tg.y) {
                     const int bit = 31 - __clz(tg.y);
                     tg.y &= ~(1u << bit);
-                    const float4 *tv = sc.tri_v8 + 3 * (size_t) (tg.x + (uint32_t) bit);
+                    const float4 *tv = wf_tri_ptr(sc, tg.x, (uint32_t) bit);
                     const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
 #if PRT_TRI_ROWS
                     if (intersect_tri_rows(rr, r8.o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
@@ -543,7 +552,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
         }
         if (mT) {
 #else
-        if (__popc(mT) > WF_COOP_MAX) {
+        if (!WF_TRI_DEFER && __popc(mT) > WF_COOP_MAX) {
             // most lanes hold triangles (small scenes, coherent rays): every lane walks its own list.  The shear rows of
             // the selection-free triangle test (intersect_tri_rows) are rebuilt here, once per list, rather than carried
             // through the traversal loop: nine more live registers spill at 64 (height field 1 875 -> 1 818 Mrays/s), and
@@ -554,7 +563,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
             while (tg.y) {
                 const int bit = 31 - __clz(tg.y);
                 tg.y &= ~(1u << bit);
-                const float4 *tv = sc.tri_v8 + 3 * (size_t) (tg.x + (uint32_t) bit);
+                const float4 *tv = wf_tri_ptr(sc, tg.x, (uint32_t) bit);
                 const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
 #if PRT_TRI_ROWS
                 if (intersect_tri_rows(rr, r8.o, xyz(a), xyz(b), xyz(c), tbest, b1, b2)) {
@@ -578,18 +587,30 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                 const unsigned v = __shfl_up_sync(FULL, incl, k);
                 if (lane >= k) incl += v;
             }
-            const unsigned total = __shfl_sync(FULL, incl, 31), off = incl - cnt;
+            const unsigned total_all = __shfl_sync(FULL, incl, 31), off = incl - cnt;
+#if WF_TRI_DEFER
+            // full rounds only while some lane still advanced through the tree this iteration; everything once nobody can
+            const bool moving = __any_sync(FULL, stepped);
+            const unsigned total = moving ? (total_all >= (unsigned) WF_TRI_DEFER ? (total_all & ~31u) : 0u) : total_all;
+#else
+            const unsigned total = total_all;
+#endif
             for (unsigned base = 0; base < total; base += 32) {
-                {
-                    const unsigned k0 = max(off, base), k1 = min(off + cnt, base + 32u);
-                    for (unsigned k = k0; k < k1; k++) so[k - base] = lane;
-                }
                 stm[lane] = 0xffffffffu;
                 sw[lane] = 32;
                 __syncwarp();
                 const unsigned p = base + lane;
                 const bool valid = p < total;
-                const int own = valid ? so[lane] : lane;
+                // owner of pair p = the first lane whose inclusive prefix exceeds p: a five-step binary search over the
+                // shuffled prefix sums (the first version had every owner write its lane id into up to 24 shared-memory
+                // slots, one store per iteration: 10 % of the kernel's instructions, ncu r02a)
+                int own = 0;
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    const unsigned v = __shfl_sync(FULL, incl, (own + step - 1) & 31);
+                    if (v <= p) own += step;
+                }
+                if (!valid) own = lane;
                 const unsigned o_off = __shfl_sync(FULL, off, own), o_mask = __shfl_sync(FULL, tg.y, own);
                 const unsigned o_base = __shfl_sync(FULL, tg.x, own);
                 const float3 ro = mk3(__shfl_sync(FULL, r8.o.x, own), __shfl_sync(FULL, r8.o.y, own), __shfl_sync(FULL, r8.o.z, own));
@@ -605,7 +626,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                 if (valid) {
                     unsigned m = o_mask;
                     for (unsigned r = p - o_off; r; r--) m &= m - 1u;
-                    const float4 *tv = sc.tri_v8 + 3 * (size_t) (o_base + (uint32_t) (__ffs(m) - 1));
+                    const float4 *tv = wf_tri_ptr(sc, o_base, (uint32_t) (__ffs(m) - 1));
                     const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
 #if PRT_TRI_ROWS
                     // same arithmetic as the per-lane branch and the megakernels (bit-identical hits across back ends);
@@ -634,8 +655,19 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                 }
                 __syncwarp();
             }
+#if WF_TRI_DEFER
+            {   // drop the pairs that were tested (the lowest set bits come first in the numbering above)
+                const unsigned done = total > off ? min(total - off, cnt) : 0u;
+                for (unsigned i = 0; i < done; i++) tg.y &= tg.y - 1u;
+                if (!busy) tg.y = 0u;
+            }
+#endif
         }
+#if WF_TRI_DEFER
+        if (busy && tg.y == 0u && ng.y <= 0x00ffffffu) {
+#else
         if (busy && ng.y <= 0x00ffffffu) {
+#endif
             if (sp > 0) {
                 --sp;
                 ng = sp < WF_SSTACK ? sstack[sp * WF_TRACE_THREADS] : gstack[sp - WF_SSTACK];
