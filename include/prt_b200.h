@@ -248,6 +248,11 @@ typedef struct {
 int prt_us_render(prt_scene *, const prt_acq_params *, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
                   uint32_t sample_stride, const prt_us_render_params *, const float *x, const float *z, float *bmode,
                   float *envelope /*nullable*/, prt_acq_stats *stats /*nullable*/);
+/* us_render() minus the acquisition, on a channel buffer that already lives on the device (e.g. the all-reduced buffer of a
+ * sample-sharded multi-GPU acquisition): pulse shaping (optional) -> delay-and-sum -> envelope -> log compression; bmode [nz][nx] and
+ * envelope [nx][nz] (nullable) are host buffers.  Synchronises `stream` before returning. */
+int prt_us_postprocess_dev(prt_context *, const prt_acq_params *, const prt_us_render_params *, const float *x, const float *z,
+                           const float *channel_dev, void *stream, float *bmode, float *envelope /*nullable*/);
 
 /* ---- "next" row f4: pulse shaping (prototype at /root/reference/RayTracingV0.py:185-204, "UltraRay Eq. 14").
  * channel [n_rows][T] of delta echoes -> out [n_rows][T] = zero-phase convolution of every row with

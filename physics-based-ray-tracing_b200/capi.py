@@ -30,7 +30,7 @@ EXPORTS = [
     "prt_scene_create", "prt_scene_destroy", "prt_scene_add_material", "prt_scene_set_material_param", "prt_scene_set_shape_transform", "prt_scene_get_stats",
     "prt_scene_add_primitive", "prt_scene_add_mesh", "prt_scene_commit", "prt_trace_closest", "prt_trace_occluded",
     "prt_ultra_bsdf_sample", "prt_directivity_weights", "prt_acquire", "prt_acquire_dev", "prt_acquire_dev_angles", "prt_acquire_variants", "prt_acquire_trace", "prt_render_path",
-    "prt_render_path_dev", "prt_render_image", "prt_film_develop_dev", "prt_das_beamform", "prt_envelope", "prt_us_render", "prt_pulse_shape", "prt_pulse_shape_dev",
+    "prt_render_path_dev", "prt_render_image", "prt_film_develop_dev", "prt_das_beamform", "prt_envelope", "prt_us_render", "prt_us_postprocess_dev", "prt_pulse_shape", "prt_pulse_shape_dev",
 ]
 
 
@@ -163,6 +163,7 @@ def load():
     L.prt_envelope.argtypes = [vp, fp, C.c_int32, C.c_int32, fp]
     L.prt_us_render.argtypes = [vp, C.POINTER(AcqParamsC), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(UsRenderParamsC),
                                 fp, fp, fp, fp, C.POINTER(AcqStatsC)]
+    L.prt_us_postprocess_dev.argtypes = [vp, C.POINTER(AcqParamsC), C.POINTER(UsRenderParamsC), fp, fp, vp, vp, fp, fp]
     L.prt_pulse_shape.argtypes = [vp, fp, C.c_uint64, C.c_int32, C.c_double, C.c_double, C.c_double, fp]
     L.prt_pulse_shape_dev.argtypes = [vp, vp, C.c_uint64, C.c_int32, C.c_double, C.c_double, C.c_double, vp, vp]
     _lib = L

@@ -79,7 +79,7 @@ __device__ __forceinline__ void init_path(const AcqDev &P, uint32_t ae, uint32_t
 // had an order), nothing else changes.
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef PRT_ACQ_CACHE
-#define PRT_ACQ_CACHE 2048                // slots per CTA (power of two; 0 = deposits go straight to global memory)
+#define PRT_ACQ_CACHE 0                   // slots per CTA (power of two, e.g. 2048; 0 = deposits go straight to global memory -- the default: measured 4 % SLOWER with the table, profiles/r02_summary.md)
 #endif
 // the mesh kernel's path stash already takes 35 KB of the 48 KB of static shared memory: it gets a quarter-size table
 #define ECHO_SLOTS(tris) ((tris) ? PRT_ACQ_CACHE / 4 : PRT_ACQ_CACHE)

@@ -185,43 +185,24 @@ __global__ void __launch_bounds__(256) k_bmode(const float *__restrict__ env, in
 
 using namespace prt;
 
-// The whole us_render() of the reference driver (/root/reference/USMain.py:92-224) behind one call, with the channel data
-// never leaving the device: acquisition (CustomIntegrator.py:235-405) -> optional pulse shaping -> delay-and-sum ->
-// envelope (USMain.py:203-208) -> log compression to the display image (:210-224).  Only the [nz][nx] image (and, if
-// asked for, the envelope) crosses the bus: 2.6 MB instead of 2 x 12.8 MB at the driver's sizes.
-extern "C" int prt_us_render(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
-                             uint32_t sample_stride, const prt_us_render_params *u, const float *x, const float *z, float *bmode,
-                             float *envelope, prt_acq_stats *stats) {
-    PRT_REQUIRE(s && p && u && x && z && bmode, "prt_us_render: null argument");
-    PRT_REQUIRE(u->nx > 0 && u->nz > 1 && u->nz <= 8192 && u->dynamic_range_db > 0, "prt_us_render: invalid image parameters");
-    if (!s->committed) { set_error("prt_us_render: scene not committed"); return PRT_ERR_STATE; }
-    prt_context *c = s->ctx;
-    std::lock_guard<std::mutex> lk(c->mtx);
-    PRT_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
+// everything us_render() does AFTER the acquisition (USMain.py:103-224), on a channel buffer that is already on the device:
+// optional pulse shaping -> delay-and-sum -> envelope -> log compression; the image (and envelope) copies are enqueued on `st`
+static int us_post(prt_context *c, const prt_acq_params *p, const prt_us_render_params *u, const float *x, const float *z,
+                   const float *channel_dev, cudaStream_t st, float *bmode, float *envelope, cudaEvent_t e_kernels) {
     const size_t n_buf = (size_t) p->n_angles * p->n_elements * (size_t) p->time_samples, n_tx = (size_t) p->n_angles * p->n_elements;
     const size_t n_px = (size_t) u->nx * u->nz;
-    int rc = ensure_scratch(c, n_buf, n_tx, (size_t) p->n_angles);
-    if (rc) return rc;
     float *ax_d = nullptr, *rf_d = nullptr, *env_d = nullptr, *img_d = nullptr, *shaped_d = nullptr;
+    int rc;
     if ((rc = scratch_slot(c, 1, sizeof(float) * ((size_t) u->nx + u->nz + 2 * (size_t) p->n_angles + 8), (void **) &ax_d))) return rc;
     if ((rc = scratch_slot(c, 2, sizeof(float) * n_px, (void **) &rf_d))) return rc;
     if ((rc = scratch_slot(c, 3, sizeof(float) * n_px, (void **) &env_d))) return rc;
     if ((rc = scratch_slot(c, 6, sizeof(float) * n_px + 16, (void **) &img_d))) return rc;
     if (u->shape_pulse && (rc = scratch_slot(c, 5, sizeof(float) * n_buf, (void **) &shaped_d))) return rc;
     unsigned *mx_d = reinterpret_cast<unsigned *>(img_d + n_px);
-    ScopedEvents<3> ev;
-    PRT_REQUIRE(ev.ok, "cudaEventCreate failed");
-    cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2];
-    PRT_CUDA(cudaEventRecord(e0, st));
-    PRT_CUDA(cudaMemsetAsync(c->acc_dev, 0, sizeof(float) * n_buf, st));
-    PRT_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(uint64_t) * 8, st));
     PRT_CUDA(cudaMemsetAsync(mx_d, 0, sizeof(unsigned), st));
-    rc = acquire_enqueue(s, p, seed, spp_total, sample_offset, sample_stride, 0, p->n_angles, c->acc_dev, c->aux_dev, c->stats_dev, st);
-    if (rc) return rc;
-    const float *ch_d = c->acc_dev;
+    const float *ch_d = channel_dev;
     if (u->shape_pulse) {
-        rc = launch_pulse(c->acc_dev, shaped_d, (uint64_t) n_tx, p->time_samples, p->fs, p->frequency, u->wave_cycles / (4.0 * p->frequency), st);
+        rc = launch_pulse(channel_dev, shaped_d, (uint64_t) n_tx, p->time_samples, p->fs, p->frequency, u->wave_cycles / (4.0 * p->frequency), st);
         if (rc) return rc;
         ch_d = shaped_d;
     }
@@ -247,9 +228,39 @@ extern "C" int prt_us_render(prt_scene *s, const prt_acq_params *p, uint64_t see
     k_env_max<<<c->sm_count * 4, 256, 0, st>>>(env_d, n_px, mx_d);
     k_bmode<<<dim3((u->nx + 31) / 32, (u->nz + 31) / 32), 256, 0, st>>>(env_d, u->nx, u->nz, mx_d, (float) u->dynamic_range_db, img_d);
     PRT_CUDA(cudaGetLastError());
-    PRT_CUDA(cudaEventRecord(e1, st));
+    if (e_kernels) PRT_CUDA(cudaEventRecord(e_kernels, st));
     PRT_CUDA(cudaMemcpyAsync(bmode, img_d, sizeof(float) * n_px, cudaMemcpyDeviceToHost, st));
     if (envelope) PRT_CUDA(cudaMemcpyAsync(envelope, env_d, sizeof(float) * n_px, cudaMemcpyDeviceToHost, st));
+    return PRT_OK;
+}
+
+// The whole us_render() of the reference driver (/root/reference/USMain.py:92-224) behind one call, with the channel data
+// never leaving the device: acquisition (CustomIntegrator.py:235-405) -> optional pulse shaping -> delay-and-sum ->
+// envelope (USMain.py:203-208) -> log compression to the display image (:210-224).  Only the [nz][nx] image (and, if
+// asked for, the envelope) crosses the bus: 2.6 MB instead of 2 x 12.8 MB at the driver's sizes.
+extern "C" int prt_us_render(prt_scene *s, const prt_acq_params *p, uint64_t seed, uint32_t spp_total, uint32_t sample_offset,
+                             uint32_t sample_stride, const prt_us_render_params *u, const float *x, const float *z, float *bmode,
+                             float *envelope, prt_acq_stats *stats) {
+    PRT_REQUIRE(s && p && u && x && z && bmode, "prt_us_render: null argument");
+    PRT_REQUIRE(u->nx > 0 && u->nz > 1 && u->nz <= 8192 && u->dynamic_range_db > 0, "prt_us_render: invalid image parameters");
+    if (!s->committed) { set_error("prt_us_render: scene not committed"); return PRT_ERR_STATE; }
+    prt_context *c = s->ctx;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    PRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t n_buf = (size_t) p->n_angles * p->n_elements * (size_t) p->time_samples, n_tx = (size_t) p->n_angles * p->n_elements;
+    int rc = ensure_scratch(c, n_buf, n_tx, (size_t) p->n_angles);
+    if (rc) return rc;
+    ScopedEvents<3> ev;
+    PRT_REQUIRE(ev.ok, "cudaEventCreate failed");
+    cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2];
+    PRT_CUDA(cudaEventRecord(e0, st));
+    PRT_CUDA(cudaMemsetAsync(c->acc_dev, 0, sizeof(float) * n_buf, st));
+    PRT_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(uint64_t) * 8, st));
+    rc = acquire_enqueue(s, p, seed, spp_total, sample_offset, sample_stride, 0, p->n_angles, c->acc_dev, c->aux_dev, c->stats_dev, st);
+    if (rc) return rc;
+    rc = us_post(c, p, u, x, z, c->acc_dev, st, bmode, envelope, e1);
+    if (rc) return rc;
     uint64_t hs[8];
     PRT_CUDA(cudaMemcpyAsync(hs, c->stats_dev, sizeof hs, cudaMemcpyDeviceToHost, st));
     PRT_CUDA(cudaEventRecord(e2, st));
@@ -261,6 +272,21 @@ extern "C" int prt_us_render(prt_scene *s, const prt_acq_params *p, uint64_t see
         stats->launches = (uint32_t) p->n_angles + 4u + (u->shape_pulse ? 1u : 0u);
         stats->_pad = 0;
     }
+    return PRT_OK;
+}
+
+// us_render() minus the acquisition, for a channel buffer that already lives on the device -- e.g. the all-reduced buffer of a
+// sample-sharded multi-GPU acquisition (distributed.acquire_sharded(to_host=False)): every rank develops the same image
+extern "C" int prt_us_postprocess_dev(prt_context *c, const prt_acq_params *p, const prt_us_render_params *u, const float *x, const float *z,
+                                      const float *channel_dev, void *stream, float *bmode, float *envelope) {
+    PRT_REQUIRE(c && p && u && x && z && channel_dev && bmode, "prt_us_postprocess_dev: null argument");
+    PRT_REQUIRE(u->nx > 0 && u->nz > 1 && u->nz <= 8192 && u->dynamic_range_db > 0, "prt_us_postprocess_dev: invalid image parameters");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    PRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    int rc = us_post(c, p, u, x, z, channel_dev, st, bmode, envelope, nullptr);
+    if (rc) return rc;
+    PRT_CUDA(cudaStreamSynchronize(st));
     return PRT_OK;
 }
 

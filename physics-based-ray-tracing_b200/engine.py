@@ -210,6 +210,21 @@ class DeviceScene:
                                    C.byref(st)), "prt_us_render")
         return img, env, st.as_dict()
 
+    def us_postprocess_dev(self, params: AcqParams, channel_ptr: int, x, z, stream: int = 0, t0: float = 0.0, f_number: float = 1.0,
+                           dynamic_range: float = 60.0, shape_pulse: bool = False, wave_cycles: float = 5.0, want_envelope: bool = True):
+        """us_render() minus the acquisition on a DEVICE channel buffer (prt_us_postprocess_dev): what a sample-sharded
+        multi-GPU acquisition feeds its all-reduced buffer to.  Returns (display_image [nz, nx], envelope [nx, nz] or None)."""
+        ps = capi.make_acq_params(params)
+        xs = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        zs = np.ascontiguousarray(z, dtype=np.float32).reshape(-1)
+        u = capi.UsRenderParamsC(xs.size, zs.size, float(t0), float(f_number), int(bool(shape_pulse)), 0, float(wave_cycles),
+                                 float(dynamic_range))
+        img = self.ctx.pinned_array((zs.size, xs.size), np.float32)
+        env = self.ctx.pinned_array((xs.size, zs.size), np.float32) if want_envelope else None
+        check(self.L.prt_us_postprocess_dev(self.ctx.h, C.byref(ps), C.byref(u), fptr(xs), fptr(zs), C.c_void_p(channel_ptr),
+                                            C.c_void_p(stream or None), fptr(img), fptr(env)), "prt_us_postprocess_dev")
+        return img, env
+
     def acquire_dev(self, params: AcqParams, buf_ptr: int, tx_ptr: int = 0, stats_ptr: int = 0, stream: int = 0,
                     seed: int = 0, spp: int = 1, sample_offset: int = 0, sample_stride: int = 1, angle_first: int = 0,
                     angle_count: Optional[int] = None, ps=None):

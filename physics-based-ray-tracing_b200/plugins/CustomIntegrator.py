@@ -150,9 +150,32 @@ class UltraIntegrator(mi.SamplingIntegrator):
         """Extension: everything us_render() of the driver does after ``scene.integrator()`` (USMain.py:99-224) --
         acquisition, delay-and-sum, envelope, log compression -- in ONE library call with the channel data resident on the
         device (prt_us_render).  Returns the driver's ``display_image`` ([len(z_scan), len(x_scan)], values in [0, 1]);
-        the envelope is left on ``self.last_envelope``.  Single GPU."""
+        the envelope is left on ``self.last_envelope``.  With an initialised process group the acquisition is
+        sample-sharded over the ranks and every rank develops the image from the all-reduced device buffer."""
         p = self.acq_params(scene)
         p.quirk_flags = self.quirk_flags
+        world = 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                world = dist.get_world_size()
+        except ImportError:
+            pass
+        if world > 1:
+            # sample shards: every rank traces its samples, the channel buffers are summed over NVLink (one all-reduce, pipelined
+            # by steering angle), and every rank develops the image from the summed buffer without it leaving the device
+            import torch
+            from prt_b200.distributed import acquire_sharded
+            dev = scene.device()
+            buf, _, stats = acquire_sharded(dev, p, seed=self.seed, spp_total=max(int(self.samples_per_element), 1), to_host=False)
+            stream = torch.cuda.current_stream(buf.device)
+            img, env = dev.us_postprocess_dev(p, buf.data_ptr(), x_scan, z_scan, stream=stream.cuda_stream, t0=t0, f_number=f_number,
+                                              dynamic_range=dynamic_range, shape_pulse=self.shape_pulse, wave_cycles=self.wave_cycles)
+            hs = stats.cpu().numpy()
+            st = dict(paths=int(hs[0]), segments=int(hs[1]), rays=int(hs[2]), deposits=int(hs[3]), misses=int(hs[4]))
+            self.last_stats, self.last_envelope = st, env
+            self.ray_count += int(st["segments"])
+            return img
         img, env, st = scene.device().us_render(p, x_scan, z_scan, seed=self.seed, spp=max(int(self.samples_per_element), 1),
                                                 t0=t0, f_number=f_number, dynamic_range=dynamic_range,
                                                 shape_pulse=self.shape_pulse, wave_cycles=self.wave_cycles)

@@ -126,6 +126,16 @@ def test_us_render_equals_the_staged_pipeline(shape_pulse):
     # clipped floor itself
     assert np.abs(img - ref).max() <= 2e-3
     assert ((img == 0) == (ref == 0)).mean() > 0.999
+    # the multi-GPU form of the same call: the acquisition lands in a DEVICE buffer (what the all-reduce of the sample shards
+    # leaves behind) and prt_us_postprocess_dev develops the image from it
+    import torch
+    from prt_b200.distributed import acquire_sharded
+    dev = scene.device()
+    p = integ.acq_params(scene)
+    buf, _, _ = acquire_sharded(dev, p, seed=integ.seed, spp_total=32, to_host=False)
+    img2, env2 = dev.us_postprocess_dev(p, buf.data_ptr(), x, z, stream=torch.cuda.current_stream().cuda_stream, f_number=1.0,
+                                        dynamic_range=60.0, shape_pulse=shape_pulse, wave_cycles=integ.wave_cycles)
+    assert np.abs(env2 - integ.last_envelope).max() <= 1e-4 * env.max() and np.abs(img2 - img).max() <= 2e-3
 
 
 def test_sharded_entry_points_single_rank():
