@@ -68,15 +68,19 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_render_path(const PtDev P) {
         uint32_t j = 0;
         bool live = false;
         for (;;) {
-            if (!live) {
-                if (!inside || j >= P.n_s) break;
+            if (!live && inside && j < P.n_s) {
                 pt_init(P, x, y, P.s_offset + j * P.s_stride, st);
                 j++;
                 cn.paths++;
                 live = true;
             }
-            live = pt_step(P, prims, st, cn);
-            if (!live) pt_splat(P.tent, tile, tx0, ty0, st.px, st.py, st.res);
+            // warp-wide exit test = the reconvergence point of every iteration (a per-lane `break` let regenerating and
+            // continuing lanes drift apart for good: see the same fix in k_acquire, prt_acquire.cu)
+            if (!__any_sync(0xffffffffu, live)) break;
+            if (live) {
+                live = pt_step(P, prims, st, cn);
+                if (!live) pt_splat(P.tent, tile, tx0, ty0, st.px, st.py, st.res);
+            }
         }
         __syncthreads();
         pt_flush_tile(P, tile, tx0, ty0);
