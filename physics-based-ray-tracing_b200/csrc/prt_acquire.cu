@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const Acq
     Counters cn = { 0, 0, 0, 0, 0 };
     PathState ps;
 #if PRT_ACQ_DEFER
-    if (TRIS) {
+    if (TRIS || PRT_ACQ_DEFER == 2) {      // 2: analytic scenes as well (A/B knob)
         // Mesh scenes: primary segments (32 parallel rays of neighbouring elements: near-identical traversals) and the
         // segments of continuing paths (scattered directions) are not mixed in one warp iteration.  A path that survives
         // its segment is parked in a per-warp shared-memory stash (ballot-compacted, 17 words, odd stride: conflict

@@ -14,5 +14,5 @@ except Exception as e:
     print("$2 FAILED", e); print(open("$1".replace(".json", ".err")).read()[-1500:])
 PY
 }
-timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/scale2_n1.json 2> gpurun_out/scale2_n1.err; show gpurun_out/scale2_n1.json N=1
+[ -n "$SKIP_N1" ] || { timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/scale2_n1.json 2> gpurun_out/scale2_n1.err; show gpurun_out/scale2_n1.json N=1; }
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/scale2_n$N.json 2> gpurun_out/scale2_n$N.err; show gpurun_out/scale2_n$N.json N=$N
