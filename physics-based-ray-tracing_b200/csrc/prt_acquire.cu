@@ -229,7 +229,11 @@ __device__ __forceinline__ const DPrim *stage_prims(const DScene &sc, DPrim *sme
 #define PRT_ACQ_WAE 1                     // warp-per-(angle, element) lane map: 0 off, 1 mesh scenes, 2 all scenes
 #endif
 #ifndef PRT_ACQ_DEFER
-#define PRT_ACQ_DEFER 1                   // mesh scenes: park continuing paths and run their segments in separate warp iterations
+#define PRT_ACQ_DEFER 2                   // park continuing paths and run their segments in separate warp iterations: 1 mesh scenes only,
+                                          // 2 all scenes.  On analytic scenes the point is not traversal coherence but PHASE: a warp whose lanes
+                                          // are all on their first segment (visible connection, deposit, sin(phase)) or all on their second
+                                          // (blocked connection, early exit) has no divergence inside the segment; mixed, the -15 degree launch
+                                          // of the headline ran 25 of 32 lanes (ncu r02p).  Headline 43.8 -> 48.5 Grays/s, others unchanged.
 #endif
 #if PRT_ACQ_DEFER
 static constexpr int ACQ_STASH_CAP = 64;  // < 32 parked before an iteration + at most 32 new ones
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(ACQ_THREADS, TRIS ? 3 : 4) k_acquire(const Acq
     Counters cn = { 0, 0, 0, 0, 0 };
     PathState ps;
 #if PRT_ACQ_DEFER
-    if (TRIS || PRT_ACQ_DEFER == 2) {      // 2: analytic scenes as well (A/B knob)
+    if (TRIS || PRT_ACQ_DEFER == 2) {
         // Mesh scenes: primary segments (32 parallel rays of neighbouring elements: near-identical traversals) and the
         // segments of continuing paths (scattered directions) are not mixed in one warp iteration.  A path that survives
         // its segment is parked in a per-warp shared-memory stash (ballot-compacted, 17 words, odd stride: conflict

@@ -123,6 +123,9 @@ struct ResScene {
     int n_prims, n_tris;
 };
 
+#ifndef PT_RES_STASH
+#define PT_RES_STASH 1              // 1: shadow rays parked in a per-warp stash and traced 32 at a time; 0: one query per lane and iteration, mixed kinds
+#endif
 #ifndef PT_RES_REGEN_MIN
 #define PT_RES_REGEN_MIN 6        // idle lanes a warp collects before it splats finished paths and starts new ones
 #endif
@@ -158,6 +161,9 @@ __global__ void __launch_bounds__(PT_THREADS, PT_RES_MINB) k_render_resident(con
     __shared__ float4 stri[3 * PT_RES_MAX_TRIS];
     __shared__ float4 tile[PT_HALO * PT_HALO];
     __shared__ unsigned s_next;
+#if PT_RES_STASH
+    __shared__ float s_stash[PT_THREADS / 32][64][12];     // < 32 parked before an E-iteration + at most 32 new ones
+#endif
     {
         const float4 *src = reinterpret_cast<const float4 *>(P.sc.prims);
         float4 *dst = reinterpret_cast<float4 *>(sprims);
@@ -176,6 +182,88 @@ __global__ void __launch_bounds__(PT_THREADS, PT_RES_MINB) k_render_resident(con
         for (int i = threadIdx.x; i < PT_HALO * PT_HALO; i += blockDim.x) tile[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (threadIdx.x == 0) s_next = 0u;
         __syncthreads();
+#if PT_RES_STASH
+        // Phase-separated warp iterations.  An E-iteration extends every live path by one segment: closest hit, pt_shade,
+        // next ray -- all lanes in the same phase.  The shadow ray a segment asks for is PARKED in a per-warp shared-memory
+        // stash together with what it will contribute (NEE radiance x MIS weight) and where (the sample's film position); an
+        // S-iteration pops 32 of them, traces them as any-hit queries and splats the unoccluded ones straight into the tile
+        // (radiance only: the sample's filter weight is added once, when its path ends).  Film accumulation is linear, so
+        // splitting a sample's radiance into its terms changes nothing but the order of the float additions.
+        PtState st;
+        bool live = false, has_res = false, dry = false;      // dry: warp-uniform
+        float(*stash)[12] = s_stash[threadIdx.x >> 5];
+        int n_st = 0;                                         // warp-uniform
+        for (;;) {
+            const unsigned m_live = __ballot_sync(FULLM, live);
+            if (n_st >= 32 || (n_st > 0 && m_live == 0u && dry)) {
+                const int take = min(n_st, 32);
+                if (lane < take) {
+                    const float *e = stash[n_st - take + lane];
+                    float tb, b1, b2;
+                    int prim, tri;
+                    cn.rays++;
+                    cn.shadow++;
+                    if (!res_query(R, mk3(e[0], e[1], e[2]), mk3(e[3], e[4], e[5]), e[6], tb, prim, tri, b1, b2))
+                        pt_splat(P.tent, tile, tx0, ty0, e[10], e[11], mk3(e[7], e[8], e[9]), 0.0f);
+                }
+                n_st -= take;
+                __syncwarp();
+                continue;
+            }
+            const unsigned idle = ~m_live;
+            if (idle && (__popc(idle) >= PT_RES_REGEN_MIN || m_live == 0u)) {
+                if (!live && has_res) {
+                    pt_splat(P.tent, tile, tx0, ty0, st.px, st.py, st.res);
+                    has_res = false;
+                }
+                if (!dry) {
+                    unsigned base = 0u;
+                    const int leader = __ffs(idle) - 1;
+                    if (lane == leader) base = atomicAdd(&s_next, (unsigned) __popc(idle));
+                    base = __shfl_sync(FULLM, base, leader);
+                    if (!live) {
+                        const unsigned item = base + __popc(idle & ((1u << lane) - 1u));
+                        if (item < n_items) {
+                            const unsigned j = item >> 8, r = item & 255u, w = r >> 5, l = r & 31u;
+                            const int x = tx0 + (int) ((w & 1u) * 8u + (l & 7u)), y = ty0 + (int) ((w >> 1) * 4u + (l >> 3));
+                            if (x < P.W && y < P.H) {
+                                pt_init(P, x, y, P.s_offset + j * P.s_stride, st);
+                                cn.paths++;
+                                live = true;
+                            }
+                        }
+                    }
+                    dry = base + (unsigned) __popc(idle) >= n_items;
+                }
+            }
+            if (!__any_sync(FULLM, live)) {
+                if (dry && n_st == 0) break;
+                continue;
+            }
+            ShadowReq sr;
+            sr.want = false;
+            if (live) {
+                float tb, b1 = 0.0f, b2 = 0.0f;
+                int prim, tri;
+                const bool hit = res_query(R, st.o, st.d, PRT_INF, tb, prim, tri, b1, b2);
+                cn.rays++;
+                Hit h;
+                if (tri >= 0) fill_tri_hit(P.sc, tri, tb, b1, b2, h);
+                else if (prim >= 0) fill_prim_hit(R.prims[prim], prim, st.o, st.d, tb, h);
+                if (hit) cn.segments++;
+                live = pt_shade(P, st, h, hit, sr);
+                has_res = !live;
+            }
+            const unsigned m_sh = __ballot_sync(FULLM, sr.want);
+            if (sr.want) {
+                float *e = stash[n_st + __popc(m_sh & ((1u << lane) - 1u))];
+                e[0] = sr.o.x; e[1] = sr.o.y; e[2] = sr.o.z; e[3] = sr.d.x; e[4] = sr.d.y; e[5] = sr.d.z; e[6] = sr.tmax;
+                e[7] = sr.c.x * sr.w; e[8] = sr.c.y * sr.w; e[9] = sr.c.z * sr.w; e[10] = st.px; e[11] = st.py;
+            }
+            n_st += __popc(m_sh);
+            __syncwarp();
+        }
+#else
         PtState st;
         ShadowReq sr;
         sr.want = false;
@@ -234,6 +322,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_RES_MINB) k_render_resident(con
                 has_res = mode == 0;
             }
         }
+#endif
         __syncthreads();
         pt_flush_tile(P, tile, tx0, ty0);
         __syncthreads();

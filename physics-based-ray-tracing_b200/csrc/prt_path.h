@@ -208,11 +208,14 @@ __device__ __forceinline__ bool pt_shade(const PtDev &P, PtState &st, const Hit 
 
 // ImageBlock::put of one finished sample into a shared-memory RGBW tile whose origin is pixel (tx0 - 1, ty0 - 1):
 // tent filter of radius 1 (pixel centres at i + 0.5) or box
-__device__ __forceinline__ void pt_splat(int tent, float4 *tile, int tx0, int ty0, float px, float py, float3 res) {
+// `wgt` scales the sample's contribution to the WEIGHT channel: 0 adds radiance only (a deferred NEE term of a sample whose
+// weight is added once, when its path ends)
+__device__ __forceinline__ void pt_splat(int tent, float4 *tile, int tx0, int ty0, float px, float py, float3 res, float wgt = 1.0f) {
     if (!tent) {
         int x = (int) floorf(px) - tx0 + 1, y = (int) floorf(py) - ty0 + 1;
         float *q = reinterpret_cast<float *>(tile + y * PT_HALO + x);
-        atomicAdd(q, res.x); atomicAdd(q + 1, res.y); atomicAdd(q + 2, res.z); atomicAdd(q + 3, 1.0f);
+        atomicAdd(q, res.x); atomicAdd(q + 1, res.y); atomicAdd(q + 2, res.z);
+        if (wgt != 0.0f) atomicAdd(q + 3, wgt);
         return;
     }
     int x0 = (int) floorf(px - 0.5f), y0 = (int) floorf(py - 0.5f);
@@ -226,7 +229,8 @@ __device__ __forceinline__ void pt_splat(int tent, float4 *tile, int tx0, int ty
             int lx = x - tx0 + 1, ly = y - ty0 + 1;
             if (w > 0.0f && lx >= 0 && ly >= 0 && lx < PT_HALO && ly < PT_HALO) {
                 float *q = reinterpret_cast<float *>(tile + ly * PT_HALO + lx);
-                atomicAdd(q, res.x * w); atomicAdd(q + 1, res.y * w); atomicAdd(q + 2, res.z * w); atomicAdd(q + 3, w);
+                atomicAdd(q, res.x * w); atomicAdd(q + 1, res.y * w); atomicAdd(q + 2, res.z * w);
+                if (wgt != 0.0f) atomicAdd(q + 3, w * wgt);
             }
         }
 }

@@ -119,6 +119,19 @@ def test_config4_cbox_full_resolution():
     img_w, img_m = film[..., :3] / film[..., 3:], mega[..., :3] / mega[..., 3:]
     for ch in range(3):
         assert _rel_mse(img_w[..., ch], img_m[..., ch]) < 1e-4
+    # oracle leg at the full resolution: one of the job's 16 sample planes (sample 3 of every pixel: the SAME PCG32 streams the
+    # full job uses for it), 4.2 M paths on the host
+    import orc_py
+    shard, sst = dev.render_path(rp, seed=4, spp=16, sample_offset=3, sample_stride=16)
+    oshard, ost = orc_py.render_path(orc_py.OracleScene(desc), rp, seed=4, spp=16, s_offset=3, s_stride=16, prec=32)
+    assert sst["paths"] == ost["paths"] == 2048 * 2048 and abs(sst["segments"] - ost["segments"]) <= 1e-3 * ost["segments"]
+    gi, oi = np.array(shard), np.asarray(oshard)
+    assert np.abs(gi[..., 3] - oi[..., 3]).max() <= 1e-4                       # filter weights: identical sample positions
+    # 8 x 8 block means (a single sample per pixel is all noise; the clipped block means are what a 1-spp plane pins)
+    blk = lambda f: np.minimum(f[..., :3] / np.maximum(f[..., 3:], 1e-30), 2.0).reshape(256, 8, 256, 8, 3).mean((1, 3))
+    bg, bo = blk(gi), blk(oi)
+    for ch in range(3):
+        assert _rel_mse(bg[..., ch], bo[..., ch]) < 1e-3
     # shards (offset g, stride 4) add up to the unsharded film
     acc = np.zeros(film.shape, dtype=np.float64)
     n_rays = 0

@@ -176,6 +176,23 @@ def test_reference_scripts_run_unchanged_up_to_the_gpu_boundary():
     assert "ModuleNotFoundError" not in r.stderr and "KeyError" not in r.stderr and "AttributeError" not in r.stderr
 
 
+def test_scene_parameters_expose_shape_transforms():
+    """mi.traverse(scene) lists '<shape id>.to_world' next to the BSDF keys; before the scene is on a device an edit lands in
+    the scene description (on a device it becomes a refit: tests/test_gpu_edges.py)."""
+    from prt_b200 import mi_compat as mi
+    from prt_b200 import scenes
+    from prt_b200.transforms import Transform4f
+    scene = mi.Scene(scenes.test_ring_scene())
+    params = mi.traverse(scene)
+    assert "ring.to_world" in params and "ring.bsdf.roughness" in params
+    T = Transform4f().translate([0.0, 0.0, 0.01]) @ Transform4f(scene.desc.shapes[0].to_world)
+    params["ring.to_world"] = T
+    assert params.update() == ["ring.to_world"]
+    assert np.allclose(scene.desc.shapes[0].to_world, T.matrix)
+    with pytest.raises(KeyError):
+        params["nosuch.to_world"] = T
+
+
 def test_packed_statistics_survive_a_float32_sum():
     """distributed.acquire_sharded sums its u64 path counters inside the float32 all-reduce of the channel buffer: packed as
     20-bit words they must come back exact for up to 16 ranks."""
