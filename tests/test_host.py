@@ -351,3 +351,35 @@ def test_gloo_world_size_2_allreduce(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_bench_line_contract_helpers():
+    """bench.py pieces that do not need a GPU: both arms build the SAME `config` object; the roofline of an on-chip scene is an
+    instruction-issue fraction that can never exceed 1 (a stale per-ray instruction count yields `stale`, not a number); the
+    HBM-resident scene reports an HBM fraction with the measured DRAM traffic beside it; an `also` entry stays small enough for
+    the four of them to survive a 1 500-character tail."""
+    import json
+    import bench
+    from prt_b200.scene import AcqParams
+    desc, label = bench.workload_desc(bench.DEFAULT_WORKLOAD)
+    p = AcqParams.from_props(desc.integrator, desc.sensor)
+    a = bench.acq_config(label, p, bench.C2_SPP, 1, desc.n_triangles(), desc.n_analytic())
+    b = bench.acq_config(label, p, bench.C2_SPP, 1, desc.n_triangles(), desc.n_analytic())
+    assert a == b and a["paths_per_gpu_per_step"] == 67109120 and "intended" in a["workload"]
+    clk = {"sm_mhz": 1965.0}
+    e = bench.ncu_entry(bench.DEFAULT_WORKLOAD)
+    assert e and e["kernel"] == "prt::k_acquire<false>" and 10 < e["warp_inst_per_ray"] < 40
+    rays = 53.7e6
+    rf = bench.roofline_block(bench.DEFAULT_WORKLOAD, "prt::k_acquire<false>", 1.1, rays, 2.56e6, clk, on_chip=True)
+    assert rf["bound"] == "issue" and 0.3 < rf["frac"] <= 1.0 and rf["unit"] == "Gwarp-inst/s" and rf["hbm"]["dram_frac"] < 1e-3
+    fast = bench.roofline_block(bench.DEFAULT_WORKLOAD, "prt::k_acquire<false>", 0.1, rays, 2.56e6, clk, on_chip=True)   # impossible rate
+    assert fast["frac"] is None and fast["stale"] is True
+    other = bench.roofline_block(bench.DEFAULT_WORKLOAD, "prt::some_other_kernel", 1.1, rays, 2.56e6, clk, on_chip=True)
+    assert other["frac"] is None and other["traffic"] is None            # a capture of a different kernel is not evidence
+    hf = bench.roofline_block("heightfield", "prt::k_wf_trace<false>", 9.3, 16.6e6, 16.6e6 * 1728, clk, on_chip=False)
+    assert hf["bound"] == "hbm" and 0.3 < hf["frac"] < 1.0 and 0.05 < hf["hbm"]["dram_frac"] < hf["frac"]
+    line = {"value": 48622.4, "msamples_per_s": 12400.4, "ms_per_step": 5.41, "n_gpus": 8, "kernel": "prt::k_wf_trace<false>",
+            "e2e": {"value": 47188.0, "host_checksum": 0.00306}, "roofline": hf, "cpu_baseline": {"value": 104.0, "cores": 16}}
+    c = bench.compact(line)
+    assert len(json.dumps(c)) < 300 and c["bound"] == "hbm" and c["n"] == 8
+    assert bench.is_pt("cbox") and bench.is_pt("heightfield:708") and not bench.is_pt("ring")
