@@ -414,7 +414,8 @@ int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri
                float4 *nodes_out, int *root_ref, prt_bvh_stats *stats, cudaStream_t st, Bvh8Out *bvh8, LbvhTopology *keep) {
     (void) ctx;
     if (keep) *keep = LbvhTopology();
-    if (bvh8) *bvh8 = Bvh8Out{ nullptr, nullptr, nullptr, 0, 0, 0.0f };
+    const uint32_t n_extra = bvh8 ? bvh8->n_extra : 0u;
+    if (bvh8) *bvh8 = Bvh8Out{ nullptr, nullptr, nullptr, 0, 0, 0.0f, n_extra };
     if (n == 0) {
         *root_ref = -1;
         return PRT_OK;
@@ -493,7 +494,7 @@ int build_lbvh(prt_context *ctx, const float4 *tri_v_in, uint32_t n, float4 *tri
         PRT_CUDA(tmp.event(&b1));
         PRT_CUDA(cudaEventRecord(b0, st));
         int rc = build_bvh8(n, tri_v_out, (const float *) nodes_out, children, ranges, &bvh8->nodes8, &bvh8->n_nodes8, &bvh8->tri_v8,
-                            &bvh8->tri8_sorted, &bvh8->levels, st);
+                            &bvh8->tri8_sorted, &bvh8->levels, st, n_extra);
         if (rc) return rc;
         PRT_CUDA(cudaEventRecord(b1, st));
         PRT_CUDA(cudaStreamSynchronize(st));
@@ -531,7 +532,8 @@ void free_topology(LbvhTopology &t) {
 
 int refit_lbvh(const LbvhTopology &t, const float4 *tri_v_sorted, float4 *nodes, prt_bvh_stats *stats, cudaStream_t st, Bvh8Out *bvh8) {
     const uint32_t n = t.n;
-    if (bvh8) *bvh8 = Bvh8Out{ nullptr, nullptr, nullptr, 0, 0, 0.0f };
+    const uint32_t n_extra = bvh8 ? bvh8->n_extra : 0u;
+    if (bvh8) *bvh8 = Bvh8Out{ nullptr, nullptr, nullptr, 0, 0, 0.0f, n_extra };
     PRT_REQUIRE(n >= 2 && t.children, "refit_lbvh: no topology was kept for this scene");
     BuildTemps tmp;
     cudaEvent_t e0, e1;
@@ -548,7 +550,7 @@ int refit_lbvh(const LbvhTopology &t, const float4 *tri_v_sorted, float4 *nodes,
     PRT_CUDA(cudaGetLastError());
     if (bvh8) {
         int rc = build_bvh8(n, tri_v_sorted, (const float *) nodes, t.children, t.ranges, &bvh8->nodes8, &bvh8->n_nodes8, &bvh8->tri_v8,
-                            &bvh8->tri8_sorted, &bvh8->levels, st);
+                            &bvh8->tri8_sorted, &bvh8->levels, st, n_extra);
         if (rc) return rc;
     }
     PRT_CUDA(cudaEventRecord(e1, st));

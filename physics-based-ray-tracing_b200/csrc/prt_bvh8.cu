@@ -191,13 +191,14 @@ int bvh8_annotate(uint32_t n, const uint32_t *tri8_sorted, const int4 *tri_info,
 // On success *out_nodes8 / *out_tri_v8 / *out_tri8_sorted are fresh device allocations owned by the caller.
 int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, const int2 *children, const int2 *ranges,
                float4 **out_nodes8, uint32_t *out_n_nodes8, float4 **out_tri_v8, uint32_t **out_tri8_sorted, int *out_levels,
-               cudaStream_t st) {
+               cudaStream_t st, uint32_t n_extra) {
     *out_nodes8 = nullptr;
     *out_tri_v8 = nullptr;
     *out_tri8_sorted = nullptr;
     *out_n_nodes8 = 0;
     *out_levels = 0;
     if (n == 0) return PRT_OK;
+    PRT_REQUIRE(n_extra == 0 || n >= 2, "build_bvh8: a super root needs a hierarchy below it");
     if (n == 1) {
         // no binary tree exists: one wide node whose slot 0 is a one-triangle leaf covering the node's whole grid
         float4 v[3];
@@ -251,15 +252,18 @@ int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, cons
     for (int pass = 0; pass < 2; pass++) {
         if (pass == 1) {
             PRT_CUDA(cudaMalloc(&nodes8, sizeof(float4) * 5 * (size_t) end));
-            PRT_CUDA(cudaMalloc(&tri_v8, sizeof(float4) * 3 * (size_t) n));
-            PRT_CUDA(cudaMalloc(&tri8_sorted, sizeof(uint32_t) * (size_t) n));
+            PRT_CUDA(cudaMalloc(&tri_v8, sizeof(float4) * 3 * ((size_t) n + n_extra)));
+            PRT_CUDA(cudaMalloc(&tri8_sorted, sizeof(uint32_t) * ((size_t) n + n_extra)));
         }
-        const int init[2] = { 1, 0 };
+        // n_extra > 0: node 0 and the first n_extra triangle records are left for the caller's super root
+        // (bvh8_write_super_root); the hierarchy's own root becomes node 1
+        const int first = n_extra ? 1 : 0;
+        const int init[2] = { first + 1, (int) n_extra };
         PRT_CUDA(cudaMemcpyAsync(counters, init, sizeof init, cudaMemcpyHostToDevice, st));
-        PRT_CUDA(cudaMemsetAsync(src, 0, sizeof(int), st));   // task 0 = binary root (node 0)
-        int begin = 0;
-        end = 1;
-        levels = 0;
+        PRT_CUDA(cudaMemsetAsync(src, 0, sizeof(int) * 2, st));   // task `first` = binary root (binary node 0)
+        int begin = first;
+        end = first + 1;
+        levels = first;
         while (begin < end) {
             const int cnt = end - begin;
             k_bvh8_level<<<(cnt + 127) / 128, 128, 0, st>>>(begin, end, src, nodes2, children, ranges, tri_v_sorted, nodes8, tri_v8,
@@ -281,6 +285,90 @@ int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, cons
     *out_tri_v8 = tri_v8;
     *out_tri8_sorted = tri8_sorted;
     *out_levels = levels;
+    return PRT_OK;
+}
+
+// Super root: triangles whose boxes span much of the scene (the walls of a room around a 10 M-triangle floor) inflate every
+// ancestor on their Morton path when they sit in the LBVH -- rays then visit leaves all over the tree (measured on BASELINE
+// config 5: 11.3 triangle tests and 13.0 node steps per ray with them in the tree; 4.5 and 9.8 for the floor alone).  They
+// are kept out of the LBVH and become LEAF CHILDREN of an extra node 0, whose one inner child is the hierarchy's root
+// (node 1): one more node step per ray, and only the oversized triangles whose own box the ray crosses are tested.
+//   big_v   host, [n_extra][3], consecutive triangles form the leaf children (ceil(n_extra / 7) each); v1.w already holds
+//           the annotation ((sorted index << 2) | shading queue)
+//   root_lo / root_hi   box of the hierarchy (node 1)
+int bvh8_write_super_root(uint32_t n_small, uint32_t n_extra, const float4 *big_v, const float root_lo[3], const float root_hi[3],
+                          float4 *nodes8, float4 *tri_v8, uint32_t *tri8_sorted, cudaStream_t st) {
+    PRT_REQUIRE(n_extra >= 1 && n_extra <= 21, "bvh8_write_super_root: 1..21 triangles");
+    const int per = (int) (n_extra + 6) / 7, n_leaf = ((int) n_extra + per - 1) / per;
+    float lo[8][3], hi[8][3];
+    int cnt[8];
+    auto pad_box = [](float *l, float *h) {
+        for (int a = 0; a < 3; a++) {
+            const float pad = 4.0f * 1.1920929e-7f * fmaxf(fmaxf(fabsf(l[a]), fabsf(h[a])), h[a] - l[a]) + 1e-30f;
+            l[a] -= pad;
+            h[a] += pad;
+        }
+    };
+    for (int a = 0; a < 3; a++) { lo[0][a] = root_lo[a]; hi[0][a] = root_hi[a]; }
+    pad_box(lo[0], hi[0]);
+    cnt[0] = 0;
+    for (int g = 0; g < n_leaf; g++) {
+        float *l = lo[1 + g], *h = hi[1 + g];
+        for (int a = 0; a < 3; a++) { l[a] = FLT_MAX; h[a] = -FLT_MAX; }
+        cnt[1 + g] = 0;
+        for (int j = g * per; j < (int) n_extra && j < (g + 1) * per; j++, cnt[1 + g]++)
+            for (int c = 0; c < 3; c++) {
+                const float4 v = big_v[3 * j + c];
+                l[0] = fminf(l[0], v.x); l[1] = fminf(l[1], v.y); l[2] = fminf(l[2], v.z);
+                h[0] = fmaxf(h[0], v.x); h[1] = fmaxf(h[1], v.y); h[2] = fmaxf(h[2], v.z);
+            }
+        pad_box(l, h);
+    }
+    const int n = 1 + n_leaf;
+    float plo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, phi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (int k = 0; k < n; k++)
+        for (int a = 0; a < 3; a++) { plo[a] = fminf(plo[a], lo[k][a]); phi[a] = fmaxf(phi[a], hi[k][a]); }
+    uint32_t eb[3];
+    float inv_step[3];
+    for (int a = 0; a < 3; a++) {       // same grid rule as k_bvh8_level
+        const float ext = fmaxf(phi[a] - plo[a], 1e-30f);
+        int e;
+        frexpf(ext / 255.0f, &e);
+        e = e > 126 ? 126 : (e < -125 ? -125 : e);
+        while (e < 126 && ceilf((phi[a] - plo[a]) * exp2f((float) -e) + 0.002f) > 255.0f) e++;
+        eb[a] = (uint32_t) (e + 127);
+        inv_step[a] = exp2f((float) -e);
+    }
+    uint32_t meta[8] = { 0 }, q[6][8];
+    for (int s = 0; s < 8; s++)
+        for (int a = 0; a < 3; a++) { q[a][s] = 255u; q[3 + a][s] = 0u; }
+    int off = 0;
+    for (int k = 0; k < n; k++) {       // child k sits in slot k: the order among ONE inner child and leaves does not matter
+        for (int a = 0; a < 3; a++) {
+            const float l = floorf((lo[k][a] - plo[a]) * inv_step[a] - 0.001f), h = ceilf((hi[k][a] - plo[a]) * inv_step[a] + 0.001f);
+            q[a][k] = (uint32_t) fminf(fmaxf(l, 0.0f), 255.0f);
+            q[3 + a][k] = (uint32_t) fminf(fmaxf(h, 0.0f), 255.0f);
+        }
+        if (k == 0) meta[k] = (1u << 5) | 24u;
+        else {
+            meta[k] = (((1u << cnt[k]) - 1u) << 5) | (uint32_t) off;
+            off += cnt[k];
+        }
+    }
+    auto bits = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+    auto pack4 = [](const uint32_t *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
+    float4 node[5];
+    node[0] = make_float4(plo[0], plo[1], plo[2], bits(eb[0] | (eb[1] << 8) | (eb[2] << 16) | (1u << 24)));   // imask: slot 0
+    node[1] = make_float4(bits(1u), bits(0u), bits(pack4(meta)), bits(pack4(meta + 4)));                        // child_base 1, tri_base 0
+    node[2] = make_float4(bits(pack4(q[0])), bits(pack4(q[0] + 4)), bits(pack4(q[1])), bits(pack4(q[1] + 4)));
+    node[3] = make_float4(bits(pack4(q[2])), bits(pack4(q[2] + 4)), bits(pack4(q[3])), bits(pack4(q[3] + 4)));
+    node[4] = make_float4(bits(pack4(q[4])), bits(pack4(q[4] + 4)), bits(pack4(q[5])), bits(pack4(q[5] + 4)));
+    uint32_t map[21];
+    for (uint32_t j = 0; j < n_extra; j++) map[j] = n_small + j;
+    PRT_CUDA(cudaMemcpyAsync(nodes8, node, sizeof node, cudaMemcpyHostToDevice, st));
+    PRT_CUDA(cudaMemcpyAsync(tri_v8, big_v, sizeof(float4) * 3 * n_extra, cudaMemcpyHostToDevice, st));
+    PRT_CUDA(cudaMemcpyAsync(tri8_sorted, map, sizeof(uint32_t) * n_extra, cudaMemcpyHostToDevice, st));
+    PRT_CUDA(cudaStreamSynchronize(st));     // the sources are host stack / caller memory
     return PRT_OK;
 }
 

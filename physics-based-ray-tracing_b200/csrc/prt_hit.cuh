@@ -29,14 +29,6 @@ __device__ __forceinline__ int traverse_bvh8(const DScene &sc, float3 o, float3 
     const Bvh8Ray r8 = bvh8_ray(o, d);
     uint2 gstack[BVH8_STACK];
     int sp = 0, best = -1;
-    if (sc.n_small < sc.n_tris) {
-#if PRT_TRI_ROWS
-        best = test_big_tris<ANY>(sc, rr, o, tbest, b1, b2);
-#else
-        best = test_big_tris<ANY>(sc, rp, o, tbest, b1, b2);
-#endif
-        if ((ANY && best >= 0) || sc.n_small == 0) return best;
-    }
     uint2 ng = make_uint2(0u, 0x80000000u);      // node group in hand: child base, hit bits | imask (root = slot 7 ^ octinv)
     for (;;) {
         uint2 tg = make_uint2(0u, 0u);

@@ -154,6 +154,7 @@ struct Bvh8Out {
     uint32_t n_nodes8;
     int levels;
     float build_ms;
+    uint32_t n_extra;     // IN: triangles the caller will hang under a super root (node 0, bvh8_write_super_root); 0 = none
 };
 // bvh8 != nullptr: also derive the compressed 8-wide BVH from the binary tree (buffers owned by the caller afterwards)
 // keep != nullptr: the topology arrays are handed to the caller instead of being freed
@@ -167,7 +168,10 @@ void free_topology(LbvhTopology &t);
 int bvh8_annotate(uint32_t n, const uint32_t *tri8_sorted, const int4 *tri_info, const DMaterial *mats, float4 *tri_v8, cudaStream_t st);
 int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, const int2 *children, const int2 *ranges,
                float4 **out_nodes8, uint32_t *out_n_nodes8, float4 **out_tri_v8, uint32_t **out_tri8_sorted, int *out_levels,
-               cudaStream_t st);
+               cudaStream_t st, uint32_t n_extra = 0);
+// node 0 of a tree built with n_extra > 0 (host side, three small uploads): see prt_bvh8.cu
+int bvh8_write_super_root(uint32_t n_small, uint32_t n_extra, const float4 *big_v, const float root_lo[3], const float root_hi[3],
+                          float4 *nodes8, float4 *tri_v8, uint32_t *tri8_sorted, cudaStream_t st);
 // exclusive prefix sum of n u32 in place; scratch: n / 2048 + 4096 words (prt_bvh.cu)
 int exclusive_scan_u32(uint32_t *data, uint32_t n, uint32_t *scratch, cudaStream_t st);
 int ensure_scratch(prt_context *ctx, size_t acc_floats, size_t aux_floats, size_t n_angles);

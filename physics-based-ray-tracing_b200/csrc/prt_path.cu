@@ -14,6 +14,7 @@
 // registers; the scene (analytic primitives in shared memory, BVH2 + triangles through the read-only path) is
 // tiny for this config and stays on chip.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "prt_hit.cuh"
@@ -483,7 +484,7 @@ static int render_host(prt_scene *s, const prt_render_params *p, uint64_t seed, 
     cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2], e3 = ev.e[3];
     PRT_CUDA(cudaEventRecord(e0, st));
     PRT_CUDA(cudaMemsetAsync(c->acc_dev, 0, sizeof(float) * n, st));
-    PRT_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(uint64_t) * 8, st));
+    PRT_CUDA(cudaMemsetAsync(c->stats_dev, 0, sizeof(uint64_t) * 16, st));
     P.film = c->acc_dev;
     P.stats = reinterpret_cast<unsigned long long *>(c->stats_dev);
     PRT_CUDA(cudaEventRecord(e1, st));
@@ -503,11 +504,15 @@ static int render_host(prt_scene *s, const prt_render_params *p, uint64_t seed, 
     cudaGetLastError();
     if (pinned_dst) pin = film_rgbw;
     PRT_CUDA(cudaMemcpyAsync(pin, src, sizeof(float) * n_out, cudaMemcpyDeviceToHost, st));
-    uint64_t hs[8];
-    PRT_CUDA(cudaMemcpyAsync(hs, c->stats_dev, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
+    uint64_t hs[16];
+    PRT_CUDA(cudaMemcpyAsync(hs, c->stats_dev, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost, st));
     PRT_CUDA(cudaEventRecord(e3, st));
     PRT_CUDA(cudaStreamSynchronize(st));
     if (!pinned_dst) memcpy(film_rgbw, pin, sizeof(float) * n_out);
+    if (getenv("PRT_WF_STATS"))     // counters of a -DWF_STATS=1 build (zero otherwise)
+        fprintf(stderr, "wf_stats rays %llu shadow %llu | ext nodes %llu tris %llu iters %llu | sh nodes %llu tris %llu iters %llu\n",
+                (unsigned long long) hs[2], (unsigned long long) hs[3], (unsigned long long) hs[4], (unsigned long long) hs[5],
+                (unsigned long long) hs[8], (unsigned long long) hs[6], (unsigned long long) hs[7], (unsigned long long) hs[9]);
     if (stats) {
         stats->paths = hs[0]; stats->segments = hs[1]; stats->rays = hs[2]; stats->shadow_rays = hs[3];
         PRT_CUDA(cudaEventElapsedTime(&stats->kernel_ms, e1, e2));

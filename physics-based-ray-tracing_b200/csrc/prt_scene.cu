@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <tuple>
 
 #include "prt_internal.h"
 
@@ -485,15 +486,6 @@ __global__ void k_xform_shape(uint32_t n, int shape, XformDev X, const int4 *__r
     }
 }
 
-// oversized triangles (DScene::n_small): v1.w = bits((sorted index << 2) | shading queue), as k_bvh8_annotate stamps the BVH8 copies
-__global__ void k_annotate_big(uint32_t first, uint32_t end, const int4 *__restrict__ tri_info, const DMaterial *__restrict__ mats,
-                               float4 *__restrict__ tri_v) {
-    const uint32_t i = first + threadIdx.x;
-    if (i >= end) return;
-    const int kind = mats[tri_info[i].z].kind;
-    const uint32_t qi = kind == PRT_MAT_DIFFUSE ? 0u : (kind == PRT_MAT_DIELECTRIC ? 1u : 2u);
-    tri_v[3 * (size_t) i + 1].w = __uint_as_float((i << 2) | qi);
-}
 }  // namespace prt
 
 extern "C" {
@@ -542,11 +534,10 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
                 hi[o] = make_int4((int) o, m.shape, m.material, (m.has_n ? 1 : 0) | (m.flip ? 2 : 0));
             }
         }
-        // Oversized triangles (bounding-box area > 1024 x the mean; at most 24, largest first) can be moved to the END of the
-        // staging arrays and kept out of the hierarchy (DScene::n_small): PRT_BIG_TRIS=1.  OFF by default -- measured on
-        // B200 (profiles/r02_summary.md): on the 10 M-triangle height field the tree gets 35 % cheaper by absolute SAH cost,
-        // but the twelve brute-force tests run when a lane fetches its ray, i.e. with 2-4 active lanes per warp, and the
-        // closest-hit kernel goes from 81 to 108 ms per step.
+        // Oversized triangles (bounding-box area > 1024 x the mean; at most 21, largest first) are moved to the END of the
+        // staging arrays and kept out of the LBVH (DScene::n_small).  The 8-wide tree hangs them under a super root as leaf
+        // children (bvh8_write_super_root: why, and what it measured); the binary traversal of the megakernels tests them
+        // ahead of the tree (test_big_tris).  PRT_BIG_TRIS=0 switches the split off.
         float blo[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, bhi[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
         uint64_t n_big = 0;
         {
@@ -566,16 +557,28 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
                 sum += area[t];
             }
             const char *e = getenv("PRT_BIG_TRIS");
-            const bool enabled = e && e[0] == '1' && nt > 64;
+            const bool enabled = !(e && e[0] == '0') && nt > 64;
             const float limit = (float) (1024.0 * sum / (double) nt);
             std::vector<uint64_t> big;
             if (enabled)
                 for (uint64_t t = 0; t < nt; t++)
                     if (area[t] > limit) big.push_back(t);
-            if (big.size() > 24) {       // the wavefront deals them out as ONE triangle group (24-bit mask)
-                std::partial_sort(big.begin(), big.begin() + 24, big.end(), [&](uint64_t a, uint64_t b) { return area[a] > area[b]; });
-                big.resize(24);
-                std::sort(big.begin(), big.end());
+            if (big.size() > 21) {       // seven leaf children of three triangles under the super root
+                std::partial_sort(big.begin(), big.begin() + 21, big.end(), [&](uint64_t a, uint64_t b) { return area[a] > area[b]; });
+                big.resize(21);
+            }
+            {   // consecutive triangles share a leaf child: order them by supporting plane (the two halves of a wall quad
+                // have the same box), then by centroid
+                auto key = [&](uint64_t t) {
+                    const float4 a = hv[3 * t], b = hv[3 * t + 1], c = hv[3 * t + 2];
+                    const float ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, vx = c.x - a.x, vy = c.y - a.y, vz = c.z - a.z;
+                    const float n[3] = { uy * vz - uz * vy, uz * vx - ux * vz, ux * vy - uy * vx };
+                    int ax = fabsf(n[0]) > fabsf(n[1]) ? 0 : 1;
+                    if (fabsf(n[2]) > fabsf(n[ax])) ax = 2;
+                    const float cen[3] = { (a.x + b.x + c.x) / 3.0f, (a.y + b.y + c.y) / 3.0f, (a.z + b.z + c.z) / 3.0f };
+                    return std::make_tuple(ax, cen[ax], cen[(ax + 1) % 3], cen[(ax + 2) % 3], t);
+                };
+                std::sort(big.begin(), big.end(), [&](uint64_t x, uint64_t y) { return key(x) < key(y); });
             }
             n_big = big.size();
             if (n_big) {
@@ -584,16 +587,17 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
                 std::vector<float4> v2(nt * 3), n2(any_n ? nt * 3 : 0);
                 std::vector<int4> i2(nt);
                 uint64_t w = 0;
-                for (int pass = 0; pass < 2; pass++)
-                    for (uint64_t t = 0; t < nt; t++)
-                        if ((int) is_big[t] == pass) {
-                            for (int c = 0; c < 3; c++) {
-                                v2[3 * w + c] = hv[3 * t + c];
-                                if (any_n) n2[3 * w + c] = hn[3 * t + c];
-                            }
-                            i2[w] = hi[t];          // .x keeps the ORIGINAL triangle index (what prt_trace_closest reports)
-                            w++;
-                        }
+                auto move = [&](uint64_t t) {
+                    for (int c = 0; c < 3; c++) {
+                        v2[3 * w + c] = hv[3 * t + c];
+                        if (any_n) n2[3 * w + c] = hn[3 * t + c];
+                    }
+                    i2[w] = hi[t];          // .x keeps the ORIGINAL triangle index (what prt_trace_closest reports)
+                    w++;
+                };
+                for (uint64_t t = 0; t < nt; t++)
+                    if (!is_big[t]) move(t);
+                for (uint64_t t : big) move(t);
                 hv.swap(v2);
                 hn.swap(n2);
                 hi.swap(i2);
@@ -620,6 +624,7 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
         PRT_CUDA(cudaMalloc(&s->nodes_dev, sizeof(float4) * 4 * (nt > 1 ? nt - 1 : 1)));
         bytes += sizeof(float4) * 3 * nt + sizeof(int4) * nt + sizeof(float4) * 4 * (nt > 1 ? nt - 1 : 1);
         Bvh8Out b8;
+        b8.n_extra = (uint32_t) n_big;
         // scenes of up to 2^22 triangles keep the tree's topology (24 B per triangle) so that a transform change can refit
         int rc = build_lbvh(s->ctx, v_in, (uint32_t) n_small, s->tri_v_dev, order, s->nodes_dev, &s->root_ref, &s->stats, st, &b8,
                             n_small <= (1u << 22) ? &s->topo : nullptr);
@@ -634,6 +639,11 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
             PRT_CUDA(cudaMemcpyAsync(s->tri_v_dev + 3 * n_small, hv.data() + 3 * n_small, sizeof(float4) * 3 * n_big, cudaMemcpyHostToDevice, st));
             PRT_CUDA(cudaStreamSynchronize(st));
         }
+        if (n_big && b8.n_nodes8) {
+            rc = bvh8_write_super_root((uint32_t) n_small, (uint32_t) n_big, hv.data() + 3 * n_small, s->stats.scene_lo, s->stats.scene_hi,
+                                       b8.nodes8, b8.tri_v8, b8.tri8_sorted, st);
+            if (rc) return rc;
+        }
         for (int k = 0; k < 3; k++) {       // bounds of ALL triangles (build_lbvh reported the hierarchy's)
             s->stats.scene_lo[k] = blo[k];
             s->stats.scene_hi[k] = bhi[k];
@@ -644,14 +654,10 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
         s->n_nodes8 = b8.n_nodes8;
         s->bvh8_levels = b8.levels;
         s->bvh8_build_ms = b8.build_ms;
-        if (b8.n_nodes8) bytes += sizeof(float4) * 5 * (size_t) b8.n_nodes8 + (sizeof(float4) * 3 + sizeof(uint32_t)) * n_small;
+        if (b8.n_nodes8) bytes += sizeof(float4) * 5 * (size_t) b8.n_nodes8 + (sizeof(float4) * 3 + sizeof(uint32_t)) * nt;
         k_gather_aux<<<(unsigned) ((nt + 255) / 256), 256, 0, st>>>(order, (uint32_t) nt, i_in, n_in, s->tri_info_dev, s->tri_n_dev);
-        rc = bvh8_annotate((uint32_t) n_small, s->tri8_sorted_dev, s->tri_info_dev, s->mats_dev, s->tri_v8_dev, st);
+        rc = bvh8_annotate((uint32_t) nt, s->tri8_sorted_dev, s->tri_info_dev, s->mats_dev, s->tri_v8_dev, st);
         if (rc) return rc;
-        if (n_big) {
-            k_annotate_big<<<1, 64, 0, st>>>((uint32_t) n_small, (uint32_t) nt, s->tri_info_dev, s->mats_dev, s->tri_v_dev);
-            PRT_CUDA(cudaGetLastError());
-        }
         PRT_CUDA(cudaStreamSynchronize(st));
         PRT_CUDA(cudaGetLastError());
         cudaFree(v_in);
@@ -755,12 +761,21 @@ int prt_scene_set_shape_transform(prt_scene *s, int shape_id, const double to_wo
         s->nodes8_dev = s->tri_v8_dev = nullptr;
         s->tri8_sorted_dev = nullptr;
         Bvh8Out b8;
+        const uint32_t n_big = s->n_tris - s->n_small;
+        b8.n_extra = n_big;
         prt_bvh_stats rs = s->stats;
         int rc = refit_lbvh(s->topo, s->tri_v_dev, s->nodes_dev, &rs, st, &b8);
         if (rc) { s->committed = false; return rc; }
         s->nodes8_dev = b8.nodes8; s->tri_v8_dev = b8.tri_v8; s->tri8_sorted_dev = b8.tri8_sorted;
         s->n_nodes8 = b8.n_nodes8; s->bvh8_levels = b8.levels;
-        rc = bvh8_annotate(s->n_small, s->tri8_sorted_dev, s->tri_info_dev, s->mats_dev, s->tri_v8_dev, st);
+        if (n_big && b8.n_nodes8) {      // the moved oversized triangles (k_xform_shape above) and the refitted root box
+            std::vector<float4> bv(3 * (size_t) n_big);
+            PRT_CUDA(cudaMemcpyAsync(bv.data(), s->tri_v_dev + 3 * (size_t) s->n_small, sizeof(float4) * 3 * n_big, cudaMemcpyDeviceToHost, st));
+            PRT_CUDA(cudaStreamSynchronize(st));
+            rc = bvh8_write_super_root(s->n_small, n_big, bv.data(), rs.scene_lo, rs.scene_hi, b8.nodes8, b8.tri_v8, b8.tri8_sorted, st);
+            if (rc) return rc;
+        }
+        rc = bvh8_annotate(s->n_tris, s->tri8_sorted_dev, s->tri_info_dev, s->mats_dev, s->tri_v8_dev, st);
         if (rc) return rc;
         s->stats.build_ms = rs.build_ms;
         s->stats.sah_cost = rs.sah_cost;

@@ -66,6 +66,9 @@ static constexpr int WF_SHADE_THREADS = 256;
 #ifndef WF_SSTACK
 #define WF_SSTACK 0                       // traversal-stack entries per lane kept in shared memory (the rest spills to local memory)
 #endif
+#ifndef WF_STATS
+#define WF_STATS 0                        // build knob: traversal counters in stats[4..9] (tools/hf_sweep.py prints them)
+#endif
 #ifndef WF_PREFETCH
 #define WF_PREFETCH 0                     // bit 0: ray records of a reserved chunk -> L2; bit 1: next node -> L1; bit 2: triangles -> L1
 #endif
@@ -249,10 +252,8 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_generate(const PtDev P,
 // ------------------------------------------------------------------------------------------------------------------
 // ray queries with dynamic fetch over the compressed 8-wide BVH
 // ------------------------------------------------------------------------------------------------------------------
-// triangle `off` of a group: base < 2^31 -> BVH8 leaf order (tri_v8); bit 31 set -> the oversized triangles in tri_v
 __device__ __forceinline__ const float4 *wf_tri_ptr(const DScene &sc, uint32_t base, uint32_t off) {
-    const float4 *arr = (base >> 31) ? sc.tri_v : sc.tri_v8;
-    return arr + 3 * (size_t) ((base & 0x7fffffffu) + off);
+    return sc.tri_v8 + 3 * (size_t) (base + off);
 }
 
 #ifndef WF_TRI_PEEL
@@ -312,7 +313,6 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
     int pool_next = 0, pool_end = 0;     // warp-uniform: queue positions this warp has reserved
     bool dry = false;                    // warp-uniform: the queue is exhausted
     bool has = false, busy = false;      // lane holds a ray / its traversal is still running
-    bool fresh = false;                  // the ray has not been tested against the oversized triangles yet
     uint32_t slot = 0, qpos = 0;         // path slot, queue position of the ray
     Bvh8Ray r8;
     r8.o = mk3(0, 0, 0); r8.inv = mk3(1, 1, 1); r8.octinv4 = 0;
@@ -326,11 +326,18 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
     uint2 tg = make_uint2(0u, 0u);              // triangle group in hand: base, 24-bit mask (consumed by the triangle phase)
     uint2 gstack[BVH8_STACK > WF_SSTACK ? BVH8_STACK - WF_SSTACK : 1];
     unsigned n_rays = 0, n_valid = 0;
+#if WF_STATS
+    unsigned n_nodes = 0, n_tris = 0, n_iter = 0;
+#endif
 
     for (;;) {
+#if WF_STATS
+        n_iter += lane == 0;
+#endif
         // ---- retire finished rays ----
         const bool fin = has && !busy;
-        if (__any_sync(FULL, fin)) {
+        const unsigned mfin = __ballot_sync(FULL, fin);
+        if (mfin && (WF_REFILL_MIN <= 1 || __popc(mfin) >= WF_REFILL_MIN || !__any_sync(FULL, busy))) {
             if (!ANY) {
                 int qi = -1;
                 if (fin) {
@@ -453,13 +460,9 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
                         }
                         if (!ANY) tbest = prim_t;
                     }
-                    // the scene's oversized triangles (DScene::n_small) are not in the hierarchy: they become this ray's FIRST
-                    // triangle group, dealt out with everybody else's leaf triangles in the triangle phase below (a loop at
-                    // this point would run with the 2-4 lanes that happen to refill together: measured 81 -> 108 ms)
-                    fresh = sc.n_small < sc.n_tris && !blocked;
                     sp = 0;
                     ng = make_uint2(0u, 0x80000000u);
-                    busy = !((sc.n_small == 0 && !fresh) || blocked);
+                    busy = sc.n_tris > 0 && !blocked;
                 }
                 pool_next += min(avail, __popc(need));
                 need = __ballot_sync(FULL, !has);
@@ -475,13 +478,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
         tg = make_uint2(0u, 0u);
 #endif
         bool stepped = false;
-        if (can_step && fresh) {
-            stepped = true;
-            // bit 31 of the base: the group lives in tri_v (sorted order, behind the n_small triangles of the tree), not in tri_v8
-            tg = make_uint2(0x80000000u | (uint32_t) sc.n_small, (1u << (sc.n_tris - sc.n_small)) - 1u);
-            fresh = false;
-            if (sc.n_small == 0) ng.y = 0u;                  // no tree at all: the traversal ends after this group
-        } else if (can_step && ng.y > 0x00ffffffu) {
+        if (can_step && ng.y > 0x00ffffffu) {
             stepped = true;
             const uint32_t hits = ng.y, imask8 = ng.y & 0xffu;
             const int bit = 31 - __clz(hits);
@@ -503,6 +500,10 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
 #endif
             ng = make_uint2(child_base, (hm & 0xff000000u) | imask);
             tg = make_uint2(tri_base, hm & 0x00ffffffu);
+#if WF_STATS
+            n_nodes++;
+            n_tris += __popc(tg.y);
+#endif
 #if WF_PREFETCH & 4
             if (tg.y) {     // the triangle tests below may be dealt to other lanes: start the fetch from the owner now
                 const float4 *tv = sc.tri_v8 + 3 * (size_t) (tg.x + (uint32_t) (31 - __clz(tg.y)));
@@ -681,6 +682,12 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(co
         for (int k = 0; k < WF_QUEUES; k++)
             for (int i = qc[2 * k] + lane; i < qc[2 * k + 1]; i += 32) B.q_mat[k][i] = WF_HOLE;
     }
+#endif
+#if WF_STATS
+    // build knob: node steps / leaf triangles handed to the triangle phase / warp iterations (x32) per query kind
+    wf_add_stat(P, ANY ? 6 : 4, n_nodes);
+    wf_add_stat(P, ANY ? 7 : 5, n_tris);
+    if (P.stats && lane == 0) atomicAdd(P.stats + (ANY ? 9 : 8), (unsigned long long) n_iter);
 #endif
     wf_add_stat(P, 2, n_rays);
     if (ANY) wf_add_stat(P, 3, n_rays);

@@ -152,7 +152,7 @@ def test_loud_failures():
 
 
 @pytest.mark.parametrize("which", ["ring", "heightfield", "analytic"])
-def test_transform_update_refits_instead_of_rebuilding(orc, which):
+def test_transform_update_refits_instead_of_rebuilding(orc, which, monkeypatch):
     """prt_scene_set_shape_transform (params['<shape>.to_world'] = T; params.update()): the moved scene must answer ray
     queries like a scene BUILT with the new transform (same primitive ids, t within 1e-5) and like the oracle; for meshes
     the update is a refit of the kept topology (same node count, no re-sort), and moving the shape back restores the
@@ -202,6 +202,17 @@ def test_transform_update_refits_instead_of_rebuilding(orc, which):
     assert (dev.trace_occluded(o, d) == (moved["prim"] >= 0)).mean() > 0.999
     if desc.n_triangles():
         assert dev.bvh_stats["n_nodes"] == nodes_before                    # same topology: refitted, not rebuilt
+    if which == "heightfield":
+        # the 8-wide tree (re-derived from the refitted binary tree, the oversized box triangles under its super root) must
+        # give the wavefront path tracer the image a freshly built scene gives it
+        assert dev.bvh_stats["n_oversized"] >= 10       # walls and ceiling (the light quad is small at this size)
+        monkeypatch.setenv("PRT_PT_MODE", "wavefront")
+        rp = scene.integrator().render_params(scene)
+        f_moved, st_moved = dev.render_path(rp, seed=3, spp=4)
+        f_fresh, st_fresh = DeviceScene(desc2).render_path(rp, seed=3, spp=4)
+        assert st_moved["paths"] == st_fresh["paths"] and abs(st_moved["segments"] - st_fresh["segments"]) <= 2e-3 * st_fresh["segments"]
+        a, b = np.array(f_moved)[..., :3], np.array(f_fresh)[..., :3]
+        assert np.mean((a - b) ** 2) <= 1e-3 * np.mean(b ** 2)
     params[f"{shape.id}.to_world"] = Transform4f(old)
     params.update()
     back = dev.trace_closest(o, d)

@@ -135,7 +135,7 @@ def test_heightfield_lbvh_against_oracle(orc):
     scene = mi.Scene(desc)
     dev = scene.device()
     st = dev.bvh_stats
-    assert st["n_triangles"] == 2 * 199 * 199 + 12
+    assert st["n_triangles"] == 2 * 199 * 199 + 12 and st["n_oversized"] == 12
     assert st["n_nodes"] == st["n_triangles"] - st["n_oversized"] - 1
     rng = np.random.default_rng(4)
     o = rng.uniform((-0.9, -0.8, -0.9), (0.9, 0.9, 0.9), size=(40000, 3)).astype(np.float32)
@@ -160,19 +160,19 @@ def test_heightfield_lbvh_against_oracle(orc):
     assert _rel_mse(gi, ci) < 1e-3
 
 
-@pytest.mark.parametrize("knob", ["big_tris", "ray_sort"])
+@pytest.mark.parametrize("knob", ["no_big_tris", "ray_sort"])
 def test_heightfield_build_and_scheduling_knobs_do_not_change_hits(orc, monkeypatch, knob):
-    """Two opt-in paths of the big-scene pipeline (both measured and left off by default, profiles/r02_summary.md) must
-    find the same hits: PRT_BIG_TRIS=1 keeps the 12 oversized box triangles out of the hierarchy (DScene::n_small) and tests
-    them one by one in every traversal (BVH2, BVH8, wavefront); PRT_WF_SORT=7 traces every bounce's rays in (origin cell,
-    octant) order through a permutation of the ray queue."""
-    if knob == "big_tris":
-        monkeypatch.setenv("PRT_BIG_TRIS", "1")
+    """Two knobs of the big-scene pipeline must find the same hits as the default: PRT_BIG_TRIS=0 puts the 12 oversized box
+    triangles back INTO the LBVH (by default they stay out of it, DScene::n_small: leaf children of the 8-wide tree's super
+    root, tested ahead of the tree by the binary traversal); PRT_WF_SORT=7 (off by default, profiles/r02_summary.md) traces
+    every bounce's rays in (origin cell, octant) order through a permutation of the ray queue."""
+    if knob == "no_big_tris":
+        monkeypatch.setenv("PRT_BIG_TRIS", "0")
     desc = scenes.heightfield_scene(200, (64, 36), 8)
     scene = mi.Scene(desc)
     dev = scene.device()
     st = dev.bvh_stats
-    assert st["n_oversized"] == (12 if knob == "big_tris" else 0)
+    assert st["n_oversized"] == (0 if knob == "no_big_tris" else 12)
     assert st["n_nodes"] == st["n_triangles"] - st["n_oversized"] - 1
     rng = np.random.default_rng(5)
     o = rng.uniform((-0.9, -0.8, -0.9), (0.9, 0.9, 0.9), size=(20000, 3)).astype(np.float32)
