@@ -16,11 +16,6 @@
 #define PRT_INF __int_as_float(0x7f800000)
 
 namespace prt {
-#ifndef PRT_NODE_F4
-#define PRT_NODE_F4 5      // float4 per node record: 5 = packed 80 B (five 128-bit loads); 6 = padded to 96 B (three 256-bit loads)
-#endif
-// 8-wide BVH node record (prt_bvh8.cuh)
-static constexpr int BVH8_NODE_F4 = PRT_NODE_F4;
 
 // ------------------------------------------------------------------------------------------------
 // device scene layout (all arrays 16-byte aligned, read through the read-only path)

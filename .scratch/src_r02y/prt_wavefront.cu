@@ -55,10 +55,7 @@ static constexpr int WF_SHADE_THREADS = 256;
 #define WF_REFILL_MIN 1                    // idle lanes before a warp goes back to the queue
 #endif
 #ifndef WF_TRACE_MINB
-#define WF_TRACE_MINB 7                   // min resident CTAs per SM the closest-hit kernel is compiled for (7: 72 registers, no spills;
-#endif                                    // measured 4 / 5 / 6 / 7 / 8 / 9 / 10: 80.3 / 65.5 / 59.2 / 59.1 / 61.2 / 63.7 / 66.2 ms per step, r03a)
-#ifndef WF_TRACE_MINB_SH
-#define WF_TRACE_MINB_SH 8                // ... and the shadow-ray kernel
+#define WF_TRACE_MINB 8                   // min resident CTAs per SM the trace kernels are compiled for
 #endif
 #ifndef WF_QCHUNK
 #define WF_QCHUNK 32                      // shading-queue entries a trace warp reserves per atomic (0: one atomic per retire event)
@@ -69,15 +66,6 @@ static constexpr int WF_SHADE_THREADS = 256;
 #ifndef WF_SSTACK
 #define WF_SSTACK 0                       // traversal-stack entries per lane kept in shared memory (the rest spills to local memory)
 #endif
-#ifndef WF_EARLY_POP
-#define WF_EARLY_POP 1                    // pop the traversal stack before the triangle phase (its load overlaps the tests):
-#endif                                    // shadow rays 30.5 -> 26.2 ms per step, closest hits unchanged (r03a)
-#ifndef WF_TOPCACHE
-#define WF_TOPCACHE 0                     // newest traversal-stack entry kept in registers
-#endif
-#ifndef WF_STEPS
-#define WF_STEPS 2                        // node steps per loop iteration of the closest-hit kernel (> 1 needs WF_EARLY_POP):
-#endif                                    // 1 / 2 / 3: 59.0 / 57.9 / 58.4 ms per step; the shadow kernel keeps 1 (26.2 / 26.7 / 27.7)
 #ifndef WF_STATS
 #define WF_STATS 0                        // build knob: traversal counters in stats[4..9] (tools/hf_sweep.py prints them)
 #endif
@@ -268,34 +256,17 @@ __device__ __forceinline__ const float4 *wf_tri_ptr(const DScene &sc, uint32_t b
     return sc.tri_v8 + 3 * (size_t) (base + off);
 }
 
-// position of the r-th (0-based) set bit of a 24-bit mask: five popc steps (the clear-lowest-bit loop this replaces ran with
-// 8.4 of 32 lanes and was 6.4 % of the closest-hit kernel's instructions, ncu r02y)
-__device__ __forceinline__ uint32_t wf_nth_set_bit(uint32_t m, uint32_t r) {
-    uint32_t pos = 0, t = __popc(m & 0xffffu);
-    if (r >= t) { r -= t; pos = 16; }
-    t = __popc((m >> pos) & 0xffu);
-    if (r >= t) { r -= t; pos += 8; }
-    t = __popc((m >> pos) & 0xfu);
-    if (r >= t) { r -= t; pos += 4; }
-    t = __popc((m >> pos) & 0x3u);
-    if (r >= t) { r -= t; pos += 2; }
-    t = (m >> pos) & 1u;
-    if (r >= t) pos += 1;
-    return pos;
-}
-
 #ifndef WF_TRI_PEEL
 #define WF_TRI_PEEL 0                    // per-lane triangle rounds only while > WF_COOP_MAX lanes have one; tails go to the cooperative test
 #endif
 #ifndef WF_TRI_DEFER
 #define WF_TRI_DEFER 0                   // > 0: a lane keeps the triangles its node step yielded and waits; the warp tests them only in
 #endif                                    // full rounds of 32 (ray, triangle) pairs, or when no lane can advance otherwise
-static_assert(WF_STEPS <= 1 || (WF_EARLY_POP && !WF_TRI_DEFER), "WF_STEPS > 1 pops inside the step loop");
 #ifndef WF_TOPN
 #define WF_TOPN 0                         // first WF_TOPN nodes of the 8-wide BVH (breadth-first: 73 = top three levels) staged in shared memory
 #endif
 template <bool ANY>
-__global__ void __launch_bounds__(WF_TRACE_THREADS, ANY ? WF_TRACE_MINB_SH : WF_TRACE_MINB) k_wf_trace(const PtDev P, const WfBuf B, const int bounce,
+__global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MINB) k_wf_trace(const PtDev P, const WfBuf B, const int bounce,
                                                                               const uint32_t *__restrict__ perm) {
     // dynamic shared memory: [analytic primitives (n_prims x 128 B; none for pure mesh scenes, which leaves that much more
     // of the SM's unified array to L1)][optionally the first WF_SSTACK traversal-stack entries of every lane, entry-major].
@@ -310,10 +281,10 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, ANY ? WF_TRACE_MINB_SH : WF_
 #if WF_TOPN
     // The top levels are fetched by every ray of every warp.  They hit in L1 anyway (ncu r01: top of the tree is < 6 KB), so
     // staging them is worth one L1 -> shared latency difference per visit, nothing more: measured in profiles/r02_summary.md
-    __shared__ float4 s_top[BVH8_NODE_F4 * WF_TOPN];
+    __shared__ float4 s_top[5 * WF_TOPN];
     {
         const int ntop = min(WF_TOPN, P.sc.n_nodes8);
-        for (int i = threadIdx.x; i < BVH8_NODE_F4 * ntop; i += blockDim.x) s_top[i] = P.sc.nodes8[i];
+        for (int i = threadIdx.x; i < 5 * ntop; i += blockDim.x) s_top[i] = P.sc.nodes8[i];
     }
 #endif
 #if WF_QCHUNK
@@ -354,9 +325,6 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, ANY ? WF_TRACE_MINB_SH : WF_
     uint2 ng = make_uint2(0, 0);                // node group in hand: child base, hit bits | imask
     uint2 tg = make_uint2(0u, 0u);              // triangle group in hand: base, 24-bit mask (consumed by the triangle phase)
     uint2 gstack[BVH8_STACK > WF_SSTACK ? BVH8_STACK - WF_SSTACK : 1];
-#if WF_TOPCACHE
-    uint2 top = make_uint2(0u, 0u);             // register copy of the newest stack entry (y == 0: empty)
-#endif
     unsigned n_rays = 0, n_valid = 0;
 #if WF_STATS
     unsigned n_nodes = 0, n_tris = 0, n_iter = 0;
@@ -493,9 +461,6 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, ANY ? WF_TRACE_MINB_SH : WF_
                         if (!ANY) tbest = prim_t;
                     }
                     sp = 0;
-#if WF_TOPCACHE
-                    top.y = 0u;
-#endif
                     ng = make_uint2(0u, 0x80000000u);
                     busy = sc.n_tris > 0 && !blocked;
                 }
@@ -513,39 +478,16 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, ANY ? WF_TRACE_MINB_SH : WF_
         tg = make_uint2(0u, 0u);
 #endif
         bool stepped = false;
-#if WF_STEPS > 1
-        // up to WF_STEPS node steps per iteration for the lanes whose last step yielded no triangles: the triangle phase and
-        // the retire / refill pass (fixed cost per iteration) are shared by more node steps
-        bool last = false;
-        for (int it = 0; it < (ANY ? 1 : WF_STEPS); it++) {
-        const bool go = can_step && !last && tg.y == 0u && ng.y > 0x00ffffffu;
-        if (it > 0 && !__any_sync(FULL, go)) break;
-        if (go) {
-            stepped = true;
-#else
         if (can_step && ng.y > 0x00ffffffu) {
             stepped = true;
-#endif
             const uint32_t hits = ng.y, imask8 = ng.y & 0xffu;
             const int bit = 31 - __clz(hits);
             ng.y &= ~(1u << bit);
-#if WF_TOPCACHE
-            // the newest stack entry lives in registers; only an entry that gets covered by a deeper one goes to memory
-            if (ng.y > 0x00ffffffu) {
-                if (top.y && sp < BVH8_STACK) {
-                    if (sp < WF_SSTACK) sstack[sp * WF_TRACE_THREADS] = top;
-                    else gstack[sp - WF_SSTACK] = top;
-                    sp++;
-                }
-                top = ng;
-            }
-#else
             if (ng.y > 0x00ffffffu && sp < BVH8_STACK) {
                 if (sp < WF_SSTACK) sstack[sp * WF_TRACE_THREADS] = ng;
                 else gstack[sp - WF_SSTACK] = ng;
                 sp++;
             }
-#endif
             const uint32_t slot_index = (uint32_t) (bit - 24) ^ (r8.octinv4 & 0xffu);
             const uint32_t rel = __popc(imask8 & ~(0xffffffffu << slot_index));
             uint32_t child_base, tri_base, imask;
@@ -569,38 +511,16 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, ANY ? WF_TRACE_MINB_SH : WF_
                 prefetch_l1(tv + 2);
             }
 #endif
-        }
-#if WF_EARLY_POP
-        // the next node group is fetched from the (local-memory) stack NOW, so that the pop's latency -- 89 % of the pops
-        // miss L1 -- runs under the triangle phase instead of in front of the next node step
-#if WF_STEPS <= 1
-        bool last = false;
-#endif
-        if (busy && !last && ng.y <= 0x00ffffffu) {
-#if WF_TOPCACHE
-            if (top.y) {
-                ng = top;
-                top.y = 0u;
-            } else
-#endif
-            if (sp > 0) {
-                --sp;
-                ng = sp < WF_SSTACK ? sstack[sp * WF_TRACE_THREADS] : gstack[sp - WF_SSTACK];
-            } else last = true;
-        }
-#if WF_STEPS > 1
-        }
-#endif
-#endif
 #if WF_PREFETCH & 2
-        if (busy && ng.y > 0x00ffffffu) {   // the node this lane visits next: its fetch overlaps the triangle phase
-            const int nb = 31 - __clz(ng.y);
-            const uint32_t si = (uint32_t) (nb - 24) ^ (r8.octinv4 & 0xffu);
-            const float4 *nn = sc.nodes8 + BVH8_NODE_F4 * (size_t) (ng.x + __popc(ng.y & 0xffu & ~(0xffffffffu << si)));
-            prefetch_l1(nn);
-            prefetch_l1(nn + 4);
-        }
+            if (ng.y > 0x00ffffffu) {   // the node this lane visits next: its fetch overlaps the triangle phase
+                const int nb = 31 - __clz(ng.y);
+                const uint32_t si = (uint32_t) (nb - 24) ^ (r8.octinv4 & 0xffu);
+                const float4 *nn = sc.nodes8 + 5 * (size_t) (ng.x + __popc(ng.y & 0xffu & ~(0xffffffffu << si)));
+                prefetch_l1(nn);
+                prefetch_l1(nn + 4);
+            }
 #endif
+        }
         // ---- the triangles those nodes yielded ----
         unsigned mT = __ballot_sync(FULL, tg.y != 0u);
 #if WF_TRI_PEEL
@@ -705,7 +625,9 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, ANY ? WF_TRACE_MINB_SH : WF_
                 int hid = -1;
                 bool hit = false;
                 if (valid) {
-                    const float4 *tv = wf_tri_ptr(sc, o_base, wf_nth_set_bit(o_mask, p - o_off));
+                    unsigned m = o_mask;
+                    for (unsigned r = p - o_off; r; r--) m &= m - 1u;
+                    const float4 *tv = wf_tri_ptr(sc, o_base, (uint32_t) (__ffs(m) - 1));
                     const float4 a = ldg4(tv), b = ldg4(tv + 1), c = ldg4(tv + 2);
 #if PRT_TRI_ROWS
                     // same arithmetic as the per-lane branch and the megakernels (bit-identical hits across back ends);
@@ -742,19 +664,10 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, ANY ? WF_TRACE_MINB_SH : WF_
             }
 #endif
         }
-#if WF_EARLY_POP
-        if (last) busy = false;
-        if (false) {
-#elif WF_TRI_DEFER
+#if WF_TRI_DEFER
         if (busy && tg.y == 0u && ng.y <= 0x00ffffffu) {
 #else
         if (busy && ng.y <= 0x00ffffffu) {
-#endif
-#if WF_TOPCACHE
-            if (top.y) {
-                ng = top;
-                top.y = 0u;
-            } else
 #endif
             if (sp > 0) {
                 --sp;

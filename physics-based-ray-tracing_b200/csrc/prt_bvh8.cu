@@ -15,7 +15,10 @@
 
 namespace prt {
 
-static constexpr int LEAF8 = 3;   // triangles per leaf child (unary count in 3 bits)
+#ifndef PRT_LEAF8
+#define PRT_LEAF8 3
+#endif
+static constexpr int LEAF8 = PRT_LEAF8;   // triangles per leaf child (unary count in 3 bits: 1 .. 3)
 
 struct Child8 {
     int   ref;       // binary-tree ref: >= 0 inner node, < 0 single triangle ~sorted index
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(128) k_bvh8_level(int begin, int end, int *__r
     }
     if (!nodes8) return;     // counting pass: only the task list and the two counters are produced
     auto pack4 = [](const uint32_t *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
-    float4 *out = nodes8 + 5 * (size_t) idx;
+    float4 *out = nodes8 + BVH8_NODE_F4 * (size_t) idx;
     out[0] = make_float4(plo[0], plo[1], plo[2], __uint_as_float(eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24)));
     out[1] = make_float4(__int_as_float(child_base), __int_as_float(tri_base), __uint_as_float(pack4(meta)), __uint_as_float(pack4(meta + 4)));
     out[2] = make_float4(__uint_as_float(pack4(q[0])), __uint_as_float(pack4(q[0] + 4)), __uint_as_float(pack4(q[1])), __uint_as_float(pack4(q[1] + 4)));
@@ -226,7 +229,7 @@ int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, cons
         node[4] = make_float4(bits(qhi), bits(0u), bits(qhi), bits(0u));
         float4 *nodes8 = nullptr, *tv8 = nullptr;
         uint32_t *map = nullptr;
-        PRT_CUDA(cudaMalloc(&nodes8, sizeof node));
+        PRT_CUDA(cudaMalloc(&nodes8, sizeof(float4) * BVH8_NODE_F4));
         PRT_CUDA(cudaMalloc(&tv8, sizeof v));
         PRT_CUDA(cudaMalloc(&map, sizeof(uint32_t)));
         PRT_CUDA(cudaMemcpy(nodes8, node, sizeof node, cudaMemcpyHostToDevice));
@@ -251,7 +254,7 @@ int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, cons
     int end = 1, levels = 0;
     for (int pass = 0; pass < 2; pass++) {
         if (pass == 1) {
-            PRT_CUDA(cudaMalloc(&nodes8, sizeof(float4) * 5 * (size_t) end));
+            PRT_CUDA(cudaMalloc(&nodes8, sizeof(float4) * BVH8_NODE_F4 * (size_t) end));
             PRT_CUDA(cudaMalloc(&tri_v8, sizeof(float4) * 3 * ((size_t) n + n_extra)));
             PRT_CUDA(cudaMalloc(&tri8_sorted, sizeof(uint32_t) * ((size_t) n + n_extra)));
         }

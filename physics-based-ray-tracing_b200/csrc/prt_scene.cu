@@ -654,7 +654,7 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
         s->n_nodes8 = b8.n_nodes8;
         s->bvh8_levels = b8.levels;
         s->bvh8_build_ms = b8.build_ms;
-        if (b8.n_nodes8) bytes += sizeof(float4) * 5 * (size_t) b8.n_nodes8 + (sizeof(float4) * 3 + sizeof(uint32_t)) * nt;
+        if (b8.n_nodes8) bytes += sizeof(float4) * BVH8_NODE_F4 * (size_t) b8.n_nodes8 + (sizeof(float4) * 3 + sizeof(uint32_t)) * nt;
         k_gather_aux<<<(unsigned) ((nt + 255) / 256), 256, 0, st>>>(order, (uint32_t) nt, i_in, n_in, s->tri_info_dev, s->tri_n_dev);
         rc = bvh8_annotate((uint32_t) nt, s->tri8_sorted_dev, s->tri_info_dev, s->mats_dev, s->tri_v8_dev, st);
         if (rc) return rc;

@@ -1,6 +1,6 @@
 """Attribute an ncu report's per-instruction counts to source lines: joins `ncu --page source --print-source sass`
 (instruction order) with `nvdisasm -g` of the same cubin (line info).  usage: ncu_by_line.py report.ncu-rep cubin mangled_name [top]"""
-import csv, io, re, subprocess, sys
+import csv, io, os, re, subprocess, sys
 rep, cubin, fun = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
@@ -30,10 +30,10 @@ for i in range(n):
     a[0] += int(data[i][ia]); a[1] += int(data[i][it]); a[2] += int(data[i][iss])
 tot = sum(a[0] for a in agg.values()); tots = sum(a[2] for a in agg.values())
 srcs = {}
-for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][2 if "--by-samples" in sys.argv else 0])[:top]:
     if f not in srcs:
         try:
-            srcs[f] = open(f"/root/repo/physics-based-ray-tracing_b200/csrc/{f}").read().splitlines()
+            srcs[f] = open(os.path.join(os.environ.get("PRT_SRC_DIR", "/root/repo/physics-based-ray-tracing_b200/csrc"), f)).read().splitlines()
         except OSError:
             srcs[f] = []
     text = srcs[f][ln - 1].strip()[:90] if 0 < ln <= len(srcs[f]) else ""
