@@ -1,0 +1,287 @@
+// prt_bvh8.cu -- GPU build of the compressed 8-wide BVH (layout: prt_bvh8.cuh) from the LBVH's binary radix tree.
+//
+// Top-down, one kernel launch per level of the wide tree: every thread turns one binary sub-tree root into one wide
+// node by repeatedly opening the child with the largest surface area until eight children are reached (sub-trees of
+// <= 3 triangles stay closed: they become leaf children), places the children in octant-ordered slots (greedy
+// assignment on dot(child centre - parent centre, slot diagonal)), quantises their boxes conservatively to 8 bits on
+// a power-of-two grid anchored at the parent box, reserves contiguous storage for its inner children and for the
+// triangles of its leaf children with two atomics, and writes the binary roots of its inner children as the tasks of
+// the next level.  The host reads one counter per level (~log8 N levels).
+#include <cfloat>
+#include <cstring>
+
+#include "prt_bvh8.cuh"
+#include "prt_internal.h"
+
+namespace prt {
+
+static constexpr int LEAF8 = 3;   // triangles per leaf child (unary count in 3 bits)
+
+struct Child8 {
+    int   ref;       // binary-tree ref: >= 0 inner node, < 0 single triangle ~sorted index
+    float lo[3], hi[3];
+};
+
+__device__ __forceinline__ int sub_count(const int2 *__restrict__ ranges, int ref) {
+    if (ref < 0) return 1;
+    const int2 r = ranges[ref];
+    return r.y - r.x + 1;
+}
+
+__global__ void __launch_bounds__(128) k_bvh8_level(int begin, int end, int *__restrict__ src, const float *__restrict__ nodes2,
+                                                    const int2 *__restrict__ children, const int2 *__restrict__ ranges,
+                                                    const float4 *__restrict__ tri_v_sorted, float4 *__restrict__ nodes8,
+                                                    float4 *__restrict__ tri_v8, uint32_t *__restrict__ tri8_sorted,
+                                                    int *__restrict__ counters) {
+    const int idx = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= end) return;
+    const int b2 = src[idx];
+    Child8 c[8];
+    int n = 2;
+    {
+        const float *rec = nodes2 + 16 * (size_t) b2;
+        const int2 ch = children[b2];
+        c[0].ref = ch.x;
+        c[1].ref = ch.y;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            c[0].lo[k] = rec[k]; c[0].hi[k] = rec[3 + k];
+            c[1].lo[k] = rec[6 + k]; c[1].hi[k] = rec[9 + k];
+        }
+    }
+    while (n < 8) {
+        int best = -1;
+        float best_a = -1.0f;
+        for (int k = 0; k < n; k++) {
+            if (c[k].ref < 0 || sub_count(ranges, c[k].ref) <= LEAF8) continue;
+            const float ex = c[k].hi[0] - c[k].lo[0], ey = c[k].hi[1] - c[k].lo[1], ez = c[k].hi[2] - c[k].lo[2];
+            const float a = ex * ey + ey * ez + ez * ex;
+            if (a > best_a) { best_a = a; best = k; }
+        }
+        if (best < 0) break;
+        const int o = c[best].ref;
+        const float *rec = nodes2 + 16 * (size_t) o;
+        const int2 ch = children[o];
+        c[best].ref = ch.x;
+        c[n].ref = ch.y;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            c[best].lo[k] = rec[k]; c[best].hi[k] = rec[3 + k];
+            c[n].lo[k] = rec[6 + k]; c[n].hi[k] = rec[9 + k];
+        }
+        n++;
+    }
+    // parent box, grid
+    float plo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, phi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (int k = 0; k < n; k++)
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            plo[a] = fminf(plo[a], c[k].lo[a]);
+            phi[a] = fmaxf(phi[a], c[k].hi[a]);
+        }
+    uint32_t eb[3];
+    float inv_step[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float ext = fmaxf(phi[a] - plo[a], 1e-30f);
+        int e;
+        frexpf(ext / 255.0f, &e);          // ext / 255 = m * 2^e, m in [0.5, 1)  ->  2^e >= ext / 255
+        e = max(min(e, 126), -125);
+        while (e < 126 && ceilf((phi[a] - plo[a]) * exp2f((float) -e) + 0.002f) > 255.0f) e++;
+        eb[a] = (uint32_t) (e + 127);
+        inv_step[a] = exp2f((float) -e);
+    }
+    // slots: greedy assignment, best (child, slot) pair first
+    int slot_of[8], child_in[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { slot_of[k] = -1; child_in[k] = -1; }
+    const float pc[3] = { 0.5f * (plo[0] + phi[0]), 0.5f * (plo[1] + phi[1]), 0.5f * (plo[2] + phi[2]) };
+    for (int it = 0; it < n; it++) {
+        float bestv = -FLT_MAX;
+        int bk = -1, bs = -1;
+        for (int k = 0; k < n; k++) {
+            if (slot_of[k] >= 0) continue;
+            const float dx = 0.5f * (c[k].lo[0] + c[k].hi[0]) - pc[0], dy = 0.5f * (c[k].lo[1] + c[k].hi[1]) - pc[1],
+                        dz = 0.5f * (c[k].lo[2] + c[k].hi[2]) - pc[2];
+            for (int s = 0; s < 8; s++) {
+                if (child_in[s] >= 0) continue;
+                const float v = ((s & 4) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 1) ? dz : -dz);
+                if (v > bestv) { bestv = v; bk = k; bs = s; }
+            }
+        }
+        slot_of[bk] = bs;
+        child_in[bs] = bk;
+    }
+    // classify, reserve storage
+    uint32_t imask = 0;
+    int n_inner = 0, n_leaf_tris = 0;
+    for (int s = 0; s < 8; s++) {
+        const int k = child_in[s];
+        if (k < 0) continue;
+        const int cnt = sub_count(ranges, c[k].ref);
+        if (c[k].ref >= 0 && cnt > LEAF8) { imask |= 1u << s; n_inner++; }
+        else n_leaf_tris += cnt;
+    }
+    const int child_base = n_inner ? atomicAdd(&counters[0], n_inner) : 0;
+    const int tri_base = n_leaf_tris ? atomicAdd(&counters[1], n_leaf_tris) : 0;
+    uint32_t meta[8], q[6][8];
+    int rel = 0, off = 0;
+    for (int s = 0; s < 8; s++) {
+        const int k = child_in[s];
+        if (k < 0) {
+            meta[s] = 0;
+#pragma unroll
+            for (int a = 0; a < 3; a++) { q[a][s] = 255u; q[3 + a][s] = 0u; }
+            continue;
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float l = floorf((c[k].lo[a] - plo[a]) * inv_step[a] - 0.001f), h = ceilf((c[k].hi[a] - plo[a]) * inv_step[a] + 0.001f);
+            q[a][s] = (uint32_t) fminf(fmaxf(l, 0.0f), 255.0f);
+            q[3 + a][s] = (uint32_t) fminf(fmaxf(h, 0.0f), 255.0f);
+        }
+        if (imask & (1u << s)) {
+            meta[s] = (1u << 5) | (24u + (uint32_t) s);
+            src[child_base + rel] = c[k].ref;
+            rel++;
+        } else {
+            const int cnt = sub_count(ranges, c[k].ref);
+            const int first = c[k].ref < 0 ? ~c[k].ref : ranges[c[k].ref].x;
+            meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t) off;
+            for (int j = 0; nodes8 && j < cnt; j++) {
+                const size_t dst = (size_t) tri_base + off + j, sidx = (size_t) first + j;
+                tri_v8[3 * dst] = tri_v_sorted[3 * sidx];
+                tri_v8[3 * dst + 1] = tri_v_sorted[3 * sidx + 1];
+                tri_v8[3 * dst + 2] = tri_v_sorted[3 * sidx + 2];
+                tri8_sorted[dst] = (uint32_t) sidx;
+            }
+            off += cnt;
+        }
+    }
+    if (!nodes8) return;     // counting pass: only the task list and the two counters are produced
+    auto pack4 = [](const uint32_t *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
+    float4 *out = nodes8 + 5 * (size_t) idx;
+    out[0] = make_float4(plo[0], plo[1], plo[2], __uint_as_float(eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24)));
+    out[1] = make_float4(__int_as_float(child_base), __int_as_float(tri_base), __uint_as_float(pack4(meta)), __uint_as_float(pack4(meta + 4)));
+    out[2] = make_float4(__uint_as_float(pack4(q[0])), __uint_as_float(pack4(q[0] + 4)), __uint_as_float(pack4(q[1])), __uint_as_float(pack4(q[1] + 4)));
+    out[3] = make_float4(__uint_as_float(pack4(q[2])), __uint_as_float(pack4(q[2] + 4)), __uint_as_float(pack4(q[3])), __uint_as_float(pack4(q[3] + 4)));
+    out[4] = make_float4(__uint_as_float(pack4(q[4])), __uint_as_float(pack4(q[4] + 4)), __uint_as_float(pack4(q[5])), __uint_as_float(pack4(q[5] + 4)));
+}
+
+// After the per-triangle tables exist (sorted order): stamp every BVH8 triangle with what a hit needs, so that retiring a
+// ray costs no dependent loads: v1.w = bits((sorted index << 2) | shading queue of its material)
+__global__ void k_bvh8_annotate(uint32_t n, const uint32_t *__restrict__ tri8_sorted, const int4 *__restrict__ tri_info,
+                                const DMaterial *__restrict__ mats, float4 *__restrict__ tri_v8) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t sorted = tri8_sorted[i];
+    const int kind = mats[tri_info[sorted].z].kind;
+    const uint32_t qi = kind == PRT_MAT_DIFFUSE ? 0u : (kind == PRT_MAT_DIELECTRIC ? 1u : 2u);
+    tri_v8[3 * (size_t) i + 1].w = __uint_as_float((sorted << 2) | qi);
+}
+
+int bvh8_annotate(uint32_t n, const uint32_t *tri8_sorted, const int4 *tri_info, const DMaterial *mats, float4 *tri_v8, cudaStream_t st) {
+    if (!n || !tri_v8) return PRT_OK;
+    k_bvh8_annotate<<<(n + 255) / 256, 256, 0, st>>>(n, tri8_sorted, tri_info, mats, tri_v8);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_OK;
+}
+
+// n >= 1 triangles.  nodes2 (16 floats / binary node, padded child boxes), children, ranges: the LBVH's arrays.
+// On success *out_nodes8 / *out_tri_v8 / *out_tri8_sorted are fresh device allocations owned by the caller.
+int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, const int2 *children, const int2 *ranges,
+               float4 **out_nodes8, uint32_t *out_n_nodes8, float4 **out_tri_v8, uint32_t **out_tri8_sorted, int *out_levels,
+               cudaStream_t st) {
+    *out_nodes8 = nullptr;
+    *out_tri_v8 = nullptr;
+    *out_tri8_sorted = nullptr;
+    *out_n_nodes8 = 0;
+    *out_levels = 0;
+    if (n == 0) return PRT_OK;
+    if (n == 1) {
+        // no binary tree exists: one wide node whose slot 0 is a one-triangle leaf covering the node's whole grid
+        float4 v[3];
+        PRT_CUDA(cudaMemcpyAsync(v, tri_v_sorted, sizeof v, cudaMemcpyDeviceToHost, st));
+        PRT_CUDA(cudaStreamSynchronize(st));
+        float lo[3] = { fminf(v[0].x, fminf(v[1].x, v[2].x)), fminf(v[0].y, fminf(v[1].y, v[2].y)), fminf(v[0].z, fminf(v[1].z, v[2].z)) };
+        float hi[3] = { fmaxf(v[0].x, fmaxf(v[1].x, v[2].x)), fmaxf(v[0].y, fmaxf(v[1].y, v[2].y)), fmaxf(v[0].z, fmaxf(v[1].z, v[2].z)) };
+        uint32_t eb[3];
+        for (int a = 0; a < 3; a++) {
+            const float pad = 4.0f * 1.1920929e-7f * fmaxf(fmaxf(fabsf(lo[a]), fabsf(hi[a])), hi[a] - lo[a]) + 1e-30f;
+            lo[a] -= pad;
+            hi[a] += pad;
+            int e;
+            frexpf(fmaxf(hi[a] - lo[a], 1e-30f) / 254.0f, &e);
+            e = e < -125 ? -125 : (e > 126 ? 126 : e);
+            eb[a] = (uint32_t) (e + 127);
+        }
+        auto bits = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+        float4 node[5];
+        node[0] = make_float4(lo[0], lo[1], lo[2], bits(eb[0] | (eb[1] << 8) | (eb[2] << 16)));
+        node[1] = make_float4(bits(0u), bits(0u), bits(1u << 5), bits(0u));
+        const uint32_t qlo = 0xffffff00u, qhi = 0x000000ffu;     // slot 0: [0, 255]; empty slots: lo 255 > hi 0
+        node[2] = make_float4(bits(qlo), bits(0xffffffffu), bits(qlo), bits(0xffffffffu));
+        node[3] = make_float4(bits(qlo), bits(0xffffffffu), bits(qhi), bits(0u));
+        node[4] = make_float4(bits(qhi), bits(0u), bits(qhi), bits(0u));
+        float4 *nodes8 = nullptr, *tv8 = nullptr;
+        uint32_t *map = nullptr;
+        PRT_CUDA(cudaMalloc(&nodes8, sizeof node));
+        PRT_CUDA(cudaMalloc(&tv8, sizeof v));
+        PRT_CUDA(cudaMalloc(&map, sizeof(uint32_t)));
+        PRT_CUDA(cudaMemcpy(nodes8, node, sizeof node, cudaMemcpyHostToDevice));
+        PRT_CUDA(cudaMemcpy(tv8, v, sizeof v, cudaMemcpyHostToDevice));
+        PRT_CUDA(cudaMemset(map, 0, sizeof(uint32_t)));
+        *out_nodes8 = nodes8;
+        *out_n_nodes8 = 1;
+        *out_tri_v8 = tv8;
+        *out_tri8_sorted = map;
+        *out_levels = 1;
+        return PRT_OK;
+    }
+    // Two passes over the same level-by-level loop: the first only counts (the wide tree has ~n/7 nodes, but the safe
+    // a-priori bound is n: an 800 MB scratch array at 10 M triangles whose cudaFree alone cost 0.7 s), the second writes
+    // into exactly sized arrays (the node count does not depend on the order in which the atomics hand out storage).
+    const size_t cap = (size_t) n;                 // tasks: every wide node opens a distinct binary node with > 3 triangles
+    float4 *nodes8 = nullptr, *tri_v8 = nullptr;
+    uint32_t *tri8_sorted = nullptr;
+    int *src = nullptr, *counters = nullptr;
+    PRT_CUDA(cudaMalloc(&src, sizeof(int) * cap));
+    PRT_CUDA(cudaMalloc(&counters, sizeof(int) * 2));
+    int end = 1, levels = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            PRT_CUDA(cudaMalloc(&nodes8, sizeof(float4) * 5 * (size_t) end));
+            PRT_CUDA(cudaMalloc(&tri_v8, sizeof(float4) * 3 * (size_t) n));
+            PRT_CUDA(cudaMalloc(&tri8_sorted, sizeof(uint32_t) * (size_t) n));
+        }
+        const int init[2] = { 1, 0 };
+        PRT_CUDA(cudaMemcpyAsync(counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+        PRT_CUDA(cudaMemsetAsync(src, 0, sizeof(int), st));   // task 0 = binary root (node 0)
+        int begin = 0;
+        end = 1;
+        levels = 0;
+        while (begin < end) {
+            const int cnt = end - begin;
+            k_bvh8_level<<<(cnt + 127) / 128, 128, 0, st>>>(begin, end, src, nodes2, children, ranges, tri_v_sorted, nodes8, tri_v8,
+                                                            tri8_sorted, counters);
+            int h[2];
+            PRT_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, st));
+            PRT_CUDA(cudaStreamSynchronize(st));
+            begin = end;
+            end = h[0];
+            levels++;
+            if (levels > 256) { set_error("build_bvh8: runaway depth"); return PRT_ERR_STATE; }
+        }
+        PRT_CUDA(cudaGetLastError());
+    }
+    cudaFree(src);
+    cudaFree(counters);
+    *out_nodes8 = nodes8;
+    *out_n_nodes8 = (uint32_t) end;
+    *out_tri_v8 = tri_v8;
+    *out_tri8_sorted = tri8_sorted;
+    *out_levels = levels;
+    return PRT_OK;
+}
+
+}  // namespace prt

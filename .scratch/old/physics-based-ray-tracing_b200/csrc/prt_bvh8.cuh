@@ -28,13 +28,6 @@ namespace prt {
 
 static constexpr int BVH8_STACK = 40;
 
-// one 32-byte load (sm_100: LDG.E.256), read-only path; p must be 32-byte aligned
-__device__ __forceinline__ void ldg8(const float4 *p, float4 &a, float4 &b) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                 : "l"(p));
-}
-
 struct Bvh8Ray {
     float3 o, inv;        // origin, 1 / direction (direction components clamped away from 0)
     uint32_t octinv4;     // (7 - octant) replicated in 4 bytes
@@ -57,16 +50,7 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
     return r;
 }
 
-#ifndef PRT_BYTEF_PRMT
-#define PRT_BYTEF_PRMT 0   // byte -> float as PRMT + FADD (ALU + FMA pipes, full rate) instead of I2F.U8 (XU pipe, quarter rate); same value
-#endif
-__device__ __forceinline__ float byte_f(uint32_t w, int j) {
-#if PRT_BYTEF_PRMT
-    return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7540u | (uint32_t) j)) - 8388608.0f;     // 2^23 + byte, exactly
-#else
-    return (float) ((w >> (8 * j)) & 0xffu);
-#endif
-}
+__device__ __forceinline__ float byte_f(uint32_t w, int j) { return (float) ((w >> (8 * j)) & 0xffu); }
 
 // tests the (up to) eight children of node `idx`; returns the hit mask: bits 24..31 = inner children at position
 // 24 + (slot ^ octinv), bits 0..23 = triangles (offsets from tri_base); writes child_base / tri_base / imask
@@ -74,17 +58,9 @@ __device__ __forceinline__ float byte_f(uint32_t w, int j) {
 template <bool PLAIN = false>
 __device__ __forceinline__ uint32_t bvh8_node(const float4 *__restrict__ nodes, uint32_t idx, const Bvh8Ray &r, float tmax,
                                               uint32_t &child_base, uint32_t &tri_base, uint32_t &imask) {
-    const float4 *n = nodes + BVH8_NODE_F4 * (size_t) idx;
-    float4 n0, n1, n2, n3, n4;
-    if (BVH8_NODE_F4 == 6 && !PLAIN) {
-        float4 unused;
-        ldg8(n, n0, n1);
-        ldg8(n + 2, n2, n3);
-        ldg8(n + 4, n4, unused);
-    } else {
-        n0 = PLAIN ? n[0] : ldg4(n); n1 = PLAIN ? n[1] : ldg4(n + 1); n2 = PLAIN ? n[2] : ldg4(n + 2);
-        n3 = PLAIN ? n[3] : ldg4(n + 3); n4 = PLAIN ? n[4] : ldg4(n + 4);
-    }
+    const float4 *n = nodes + 5 * (size_t) idx;
+    const float4 n0 = PLAIN ? n[0] : ldg4(n), n1 = PLAIN ? n[1] : ldg4(n + 1), n2 = PLAIN ? n[2] : ldg4(n + 2),
+                 n3 = PLAIN ? n[3] : ldg4(n + 3), n4 = PLAIN ? n[4] : ldg4(n + 4);
     const uint32_t e = __float_as_uint(n0.w);
     imask = e >> 24;
     child_base = __float_as_uint(n1.x);
