@@ -9,6 +9,7 @@
 // the next level.  The host reads one counter per level (~log8 N levels).
 #include <cfloat>
 #include <cstring>
+#include <string>
 
 #include "prt_bvh8.cuh"
 #include "prt_internal.h"
@@ -283,6 +284,14 @@ int build_bvh8(uint32_t n, const float4 *tri_v_sorted, const float *nodes2, cons
     }
     cudaFree(src);
     cudaFree(counters);
+    if (levels > BVH8_STACK) {      // one stack entry per level at most: deeper trees would drop subtrees silently
+        cudaFree(nodes8);
+        cudaFree(tri_v8);
+        cudaFree(tri8_sorted);
+        set_error("build_bvh8: the 8-wide tree is " + std::to_string(levels) + " levels deep; the traversal stack holds " +
+                  std::to_string(BVH8_STACK));
+        return PRT_ERR_UNSUPPORTED;
+    }
     *out_nodes8 = nodes8;
     *out_n_nodes8 = (uint32_t) end;
     *out_tri_v8 = tri_v8;
