@@ -608,13 +608,23 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
         float4 *v_in = nullptr, *n_in = nullptr;
         int4 *i_in = nullptr;
         uint32_t *order = nullptr;
-        PRT_CUDA(cudaMalloc(&v_in, sizeof(float4) * 3 * nt));
-        PRT_CUDA(cudaMalloc(&i_in, sizeof(int4) * nt));
-        PRT_CUDA(cudaMalloc(&order, sizeof(uint32_t) * nt));
+        struct Staging {       // input-order copies, freed on every way out of this block
+            void *p[4] = { nullptr, nullptr, nullptr, nullptr };
+            int n = 0;
+            cudaError_t alloc(void **out, size_t b) {
+                const cudaError_t e = cudaMalloc(out, b);
+                if (e == cudaSuccess) p[n++] = *out;
+                return e;
+            }
+            ~Staging() { for (int i = 0; i < n; i++) cudaFree(p[i]); }
+        } staging;
+        PRT_CUDA(staging.alloc((void **) &v_in, sizeof(float4) * 3 * nt));
+        PRT_CUDA(staging.alloc((void **) &i_in, sizeof(int4) * nt));
+        PRT_CUDA(staging.alloc((void **) &order, sizeof(uint32_t) * nt));
         PRT_CUDA(cudaMemcpy(v_in, hv.data(), sizeof(float4) * 3 * nt, cudaMemcpyHostToDevice));
         PRT_CUDA(cudaMemcpy(i_in, hi.data(), sizeof(int4) * nt, cudaMemcpyHostToDevice));
         if (any_n) {
-            PRT_CUDA(cudaMalloc(&n_in, sizeof(float4) * 3 * nt));
+            PRT_CUDA(staging.alloc((void **) &n_in, sizeof(float4) * 3 * nt));
             PRT_CUDA(cudaMemcpy(n_in, hn.data(), sizeof(float4) * 3 * nt, cudaMemcpyHostToDevice));
             PRT_CUDA(cudaMalloc(&s->tri_n_dev, sizeof(float4) * 3 * nt));
             bytes += sizeof(float4) * 3 * nt;
@@ -639,6 +649,9 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
             PRT_CUDA(cudaMemcpyAsync(s->tri_v_dev + 3 * n_small, hv.data() + 3 * n_small, sizeof(float4) * 3 * n_big, cudaMemcpyHostToDevice, st));
             PRT_CUDA(cudaStreamSynchronize(st));
         }
+        s->nodes8_dev = b8.nodes8;          // owned by the scene from here on (freed with it, also on the error paths below)
+        s->tri_v8_dev = b8.tri_v8;
+        s->tri8_sorted_dev = b8.tri8_sorted;
         if (n_big && b8.n_nodes8) {
             rc = bvh8_write_super_root((uint32_t) n_small, (uint32_t) n_big, hv.data() + 3 * n_small, s->stats.scene_lo, s->stats.scene_hi,
                                        b8.nodes8, b8.tri_v8, b8.tri8_sorted, st);
@@ -648,9 +661,6 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
             s->stats.scene_lo[k] = blo[k];
             s->stats.scene_hi[k] = bhi[k];
         }
-        s->nodes8_dev = b8.nodes8;
-        s->tri_v8_dev = b8.tri_v8;
-        s->tri8_sorted_dev = b8.tri8_sorted;
         s->n_nodes8 = b8.n_nodes8;
         s->bvh8_levels = b8.levels;
         s->bvh8_build_ms = b8.build_ms;
@@ -660,10 +670,6 @@ int prt_scene_commit(prt_scene *s, prt_bvh_stats *out) {
         if (rc) return rc;
         PRT_CUDA(cudaStreamSynchronize(st));
         PRT_CUDA(cudaGetLastError());
-        cudaFree(v_in);
-        cudaFree(i_in);
-        cudaFree(order);
-        if (n_in) cudaFree(n_in);
         s->n_nodes = s->stats.n_nodes;
     }
     {
