@@ -3,6 +3,7 @@
 import numpy as np
 import pytest
 
+from prt_b200.scene import load_dict_desc
 from prt_b200 import mi_compat as mi
 from prt_b200 import scenes
 
@@ -192,6 +193,48 @@ def test_heightfield_build_and_scheduling_knobs_do_not_change_hits(orc, monkeypa
         film, fst = dev.render_path(rp, seed=1, spp=8)
         assert fst["paths"] == rst["paths"] and abs(fst["segments"] - rst["segments"]) <= 2e-3 * rst["segments"]
         assert _rel_mse(_image(film), _image(ref)) < 1e-3
+
+
+@pytest.mark.parametrize("n_baffles", [3, 9, 17, 30])
+def test_super_root_groups_of_oversized_triangles(orc, monkeypatch, n_baffles):
+    """The 8-wide tree's super root holds up to 21 oversized triangles as 7 leaf children of ceil(n / 7) triangles
+    (bvh8_write_super_root).  An open height field under its light quad (2 triangles) with 3 / 9 / 17 / 30 large baffle
+    triangles gives 5 / 11 / 19 oversized triangles -- leaf children of 1, 2 and 3 -- and the cap of 21 (the rest stay in the
+    LBVH).  The wavefront path tracer (8-wide tree) must give the film of the tile megakernel (binary tree + the oversized
+    triangles tested ahead of it) and agree with the oracle."""
+    d = scenes.heightfield_scene_dict(300, (48, 27), 4)
+    for wall in ("ceiling", "back", "left", "right", "front"):
+        del d[wall]
+    rng = np.random.default_rng(11)
+    for k in range(n_baffles):          # big thin triangles hanging over the field, crossing each other; box area >= 0.81
+        c = rng.uniform((-0.6, -0.5, -0.6), (0.6, 0.3, 0.6))
+        t = rng.uniform(-0.15, 0.15, size=3)
+        v = np.array([[-0.45, t[0], -0.45], [0.45, t[1], -0.45], [0.0, t[2], 0.45]])
+        v = np.roll(v, k % 3, axis=1) + c
+        d[f"baffle{k}"] = {"type": "mesh", "vertices": v.astype(np.float64), "normals": None,
+                           "faces": np.array([[0, 1, 2]], dtype=np.uint32), "bsdf": {"type": "ref", "id": "grey"}}
+    desc = load_dict_desc(d)
+    scene = mi.Scene(desc)
+    dev = scene.device()
+    st = dev.bvh_stats
+    assert st["n_oversized"] == min(n_baffles + 2, 21)
+    assert st["n_nodes"] == st["n_triangles"] - st["n_oversized"] - 1
+    o = rng.uniform((-0.9, -0.8, -0.9), (0.9, 0.9, 0.9), size=(20000, 3)).astype(np.float32)
+    dd = rng.normal(size=(20000, 3)); dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    dd = dd.astype(np.float32)
+    osc = orc.OracleScene(desc)
+    g, c = dev.trace_closest(o, dd), osc.trace_closest(o, dd, prec=32)
+    assert (g["prim"] == c["prim"]).mean() > 0.998 and 0.1 < (g["prim"] >= 0).mean() < 1.0
+    rp = scene.integrator().render_params(scene)
+    a, sa = _render_mode(dev, rp, "mega", monkeypatch, seed=5, spp=4)
+    b, sb = _render_mode(dev, rp, "wavefront", monkeypatch, seed=5, spp=4)
+    for k in ("paths", "segments", "rays", "shadow_rays"):
+        assert sa[k] == sb[k], k
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+    ref, rst = orc.render_path(osc, rp, seed=5, spp=4, prec=32)
+    assert sb["paths"] == rst["paths"] and abs(sb["segments"] - rst["segments"]) <= 2e-3 * rst["segments"]
+    assert _image(ref).mean() > 1e-5                                   # the baffles must not black the image out
+    assert _rel_mse(_image(b), _image(ref)) < 1e-3
 
 
 def _render_mode(dev, rp, mode, monkeypatch, batch=None, **kw):
