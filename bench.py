@@ -160,6 +160,8 @@ def roofline_block(workload, kernel, launch_ms, rays_per_launch, alg_bytes, clk,
         scale = rays_per_launch / e["rays_per_launch"] if e.get("rays_per_launch") else 1.0
         hbm["dram_gbs"] = traffic * scale / sec / 1e9
         hbm["dram_frac"] = hbm["dram_gbs"] / peak_hbm
+        if e.get("l2_hit_pct") is not None:       # of the captured launch: BVH node / triangle fetches dominate its sectors
+            hbm["l2_hit_pct"], hbm["l1_hit_pct"] = e["l2_hit_pct"], e.get("l1_hit_pct")
     if on_chip:
         mhz = (clk or {}).get("sm_mhz") or sm_max
         peak = N_SM * SCHEDULERS * mhz * 1e6 / 1e9
@@ -520,6 +522,8 @@ def compact(line):
            "ms": r(line["ms_per_step"]), "n": line["n_gpus"], "ck": r(line["e2e"]["host_checksum"], 3),
            "kernel": line["kernel"].replace("prt::", ""), "bound": rf["bound"], "frac": r(rf.get("frac"), 3),
            "dram_frac": r(rf["hbm"].get("dram_frac"), 3)}
+    if rf["bound"] == "hbm" and rf["hbm"].get("l2_hit_pct") is not None:
+        out["l2_hit"] = rf["hbm"]["l2_hit_pct"]      # ncu, BVH-fetch kernel (north star: "L2 hit rate for BVH fetches")
     if "cpu_baseline" in line:
         out["cpu"] = r(line["cpu_baseline"]["value"])
         out["cpu_cores"] = line["cpu_baseline"]["cores"]
