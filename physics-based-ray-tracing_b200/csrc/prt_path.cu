@@ -121,8 +121,9 @@ static constexpr int PT_RES_MAX_TRIS = 64;
 struct ResScene {
     const DPrim *prims;      // shared memory
     const float4 *tv;        // shared memory: [n_tris][3] vertices, sorted order (v1.w unused here)
-    const float4 *bx;        // shared memory: [n_tris][2] padded bounding box of each triangle (lo, hi)
-    int n_prims, n_tris;
+    const float4 *bx;        // shared memory: [n_boxes][2] distinct padded triangle boxes (lo, hi) ...
+    const unsigned long long *bm;   // ... and the triangles each of them bounds (the two halves of a quad share one)
+    int n_prims, n_tris, n_boxes;
 };
 
 #ifndef PT_RES_CULL
@@ -154,9 +155,9 @@ __device__ __forceinline__ bool res_query(const ResScene &R, float3 o, float3 d,
     // give the same hits, ties included.  In a room every ray leaves through ONE wall: 2-3 candidates out of 12.
     const float3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     unsigned long long cand = 0ull;
-    for (int j = 0; j < R.n_tris; j++) {
-        const float4 lo = R.bx[2 * j], hi = R.bx[2 * j + 1];
-        if (box_entry(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, o, inv, tb) < PRT_INF) cand |= 1ull << j;
+    for (int u = 0; u < R.n_boxes; u++) {
+        const float4 lo = R.bx[2 * u], hi = R.bx[2 * u + 1];
+        if (box_entry(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, o, inv, tb) < PRT_INF) cand |= R.bm[u];
     }
     while (cand) {
         const int j = __ffsll((long long) cand) - 1;
@@ -184,6 +185,8 @@ __global__ void __launch_bounds__(PT_THREADS, PT_RES_MINB) k_render_resident(con
     __shared__ DPrim sprims[MAX_SMEM_PRIMS];
     __shared__ float4 stri[3 * PT_RES_MAX_TRIS];
     __shared__ float4 sbox[2 * PT_RES_MAX_TRIS];
+    __shared__ unsigned long long sbmask[PT_RES_MAX_TRIS];
+    __shared__ int s_nbox;
     __shared__ float4 tile[PT_HALO * PT_HALO];
     __shared__ unsigned s_next;
 #if PT_RES_STASH
@@ -194,22 +197,36 @@ __global__ void __launch_bounds__(PT_THREADS, PT_RES_MINB) k_render_resident(con
         float4 *dst = reinterpret_cast<float4 *>(sprims);
         for (int i = threadIdx.x; i < P.sc.n_prims * (int) (sizeof(DPrim) / 16); i += blockDim.x) dst[i] = src[i];
         for (int i = threadIdx.x; i < 3 * P.sc.n_tris; i += blockDim.x) stri[i] = P.sc.tri_v[i];
-        for (int j = threadIdx.x; j < P.sc.n_tris; j += blockDim.x) {       // per-triangle boxes, padded by a few ulps
-            const float4 a = P.sc.tri_v[3 * j], b = P.sc.tri_v[3 * j + 1], c = P.sc.tri_v[3 * j + 2];
-            float lo[3] = { fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)) };
-            float hi[3] = { fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)) };
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const float pad = 8.0f * 1.1920929e-7f * fmaxf(fmaxf(fabsf(lo[k]), fabsf(hi[k])), hi[k] - lo[k]) + 1e-30f;
-                lo[k] -= pad;
-                hi[k] += pad;
+        if (threadIdx.x == 0) {      // distinct triangle boxes, padded by a few ulps (<= 64 triangles: a few microseconds, once per CTA)
+            int nb = 0;
+            for (int j = 0; j < P.sc.n_tris; j++) {
+                const float4 a = P.sc.tri_v[3 * j], b = P.sc.tri_v[3 * j + 1], c = P.sc.tri_v[3 * j + 2];
+                float lo[3] = { fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)) };
+                float hi[3] = { fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)) };
+                for (int k = 0; k < 3; k++) {
+                    const float pad = 8.0f * 1.1920929e-7f * fmaxf(fmaxf(fabsf(lo[k]), fabsf(hi[k])), hi[k] - lo[k]) + 1e-30f;
+                    lo[k] -= pad;
+                    hi[k] += pad;
+                }
+                int u = 0;
+                for (; u < nb; u++) {
+                    const float4 l = sbox[2 * u], h = sbox[2 * u + 1];
+                    if (l.x == lo[0] && l.y == lo[1] && l.z == lo[2] && h.x == hi[0] && h.y == hi[1] && h.z == hi[2]) break;
+                }
+                if (u == nb) {
+                    sbox[2 * u] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+                    sbox[2 * u + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+                    sbmask[u] = 0ull;
+                    nb++;
+                }
+                sbmask[u] |= 1ull << j;
             }
-            sbox[2 * j] = make_float4(lo[0], lo[1], lo[2], 0.0f);
-            sbox[2 * j + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+            s_nbox = nb;
         }
     }
+    __syncthreads();
     ResScene R;
-    R.prims = sprims; R.tv = stri; R.bx = sbox; R.n_prims = P.sc.n_prims; R.n_tris = P.sc.n_tris;
+    R.prims = sprims; R.tv = stri; R.bx = sbox; R.bm = sbmask; R.n_prims = P.sc.n_prims; R.n_tris = P.sc.n_tris; R.n_boxes = s_nbox;
     const int lane = threadIdx.x & 31;
     const unsigned FULLM = 0xffffffffu;
     PtCounters cn = { 0, 0, 0, 0 };
