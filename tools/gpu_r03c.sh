@@ -2,7 +2,7 @@
 # r03c: verification of the build with the super root + new trace-kernel defaults: suite, smoke, bench, hf captures + launch list
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-TAG=r03c
+TAG=r03k
 python -m pytest tests -q -m gpu 2>&1 | tail -4 | tee gpurun_out/${TAG}_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/${TAG}_smoke.log
 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 1500 gpurun_out/${TAG}_bench.json; echo; tail -3 gpurun_out/${TAG}_bench.err
