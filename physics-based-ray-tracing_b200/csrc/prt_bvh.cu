@@ -12,7 +12,10 @@
 
 namespace prt {
 
-static constexpr int MAX_LEAF = 4;
+#ifndef PRT_MAX_LEAF
+#define PRT_MAX_LEAF 4
+#endif
+static constexpr int MAX_LEAF = PRT_MAX_LEAF;   // triangles per BVH2 leaf (the leaf ref encodes count - 1 in two bits)
 
 // ---- order-preserving float <-> uint mapping for atomicMin/Max --------------------------------
 __device__ __forceinline__ unsigned f2ord(float f) {
