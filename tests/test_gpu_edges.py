@@ -151,7 +151,7 @@ def test_loud_failures():
     assert L.prt_scene_commit(None, None) != 0 and L.prt_last_error()
 
 
-@pytest.mark.parametrize("which", ["ring", "heightfield", "analytic"])
+@pytest.mark.parametrize("which", ["ring", "heightfield", "heightfield_wall", "analytic"])
 def test_transform_update_refits_instead_of_rebuilding(orc, which, monkeypatch):
     """prt_scene_set_shape_transform (params['<shape>.to_world'] = T; params.update()): the moved scene must answer ray
     queries like a scene BUILT with the new transform (same primitive ids, t within 1e-5) and like the oracle; for meshes
@@ -165,6 +165,8 @@ def test_transform_update_refits_instead_of_rebuilding(orc, which, monkeypatch):
         desc, sid = scenes.test_ring_scene(), "ring"
     elif which == "heightfield":
         desc, sid = scenes.heightfield_scene(120, (32, 18), 1), None
+    elif which == "heightfield_wall":       # the moved shape consists of OVERSIZED triangles (outside the LBVH, under the super root)
+        desc, sid = scenes.heightfield_scene(120, (32, 18), 1), "back"
     else:
         desc, sid = scenes.ultrasound_scene("Sphere_Box", "intended"), None
     scene = mi.Scene(desc)
@@ -202,7 +204,7 @@ def test_transform_update_refits_instead_of_rebuilding(orc, which, monkeypatch):
     assert (dev.trace_occluded(o, d) == (moved["prim"] >= 0)).mean() > 0.999
     if desc.n_triangles():
         assert dev.bvh_stats["n_nodes"] == nodes_before                    # same topology: refitted, not rebuilt
-    if which == "heightfield":
+    if which.startswith("heightfield"):
         # the 8-wide tree (re-derived from the refitted binary tree, the oversized box triangles under its super root) must
         # give the wavefront path tracer the image a freshly built scene gives it
         assert dev.bvh_stats["n_oversized"] >= 10       # walls and ceiling (the light quad is small at this size)
