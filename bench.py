@@ -19,7 +19,9 @@ all-reduce of the 12.8 MB channel buffer, issued per steering-angle slice so tha
             ncu capture x this run's rays/s), peak = 4 schedulers x 148 SMs x the SM clock sampled during the run; the
             DRAM-traffic view is reported beside it (`hbm`).  Only the 10 M-triangle scene is HBM-bound (`bound: "hbm"`).
   also      the other BASELINE configs, measured briefly in the same job at the same N (compact entries, last in the line):
-            sphere_box (Mitsuba rule, degenerate), ring (config 3), cbox (config 4), heightfield (config 5)
+            sphere_box (Mitsuba rule, degenerate), ring (config 3), cbox (config 4), heightfield (config 5); at N = 1 also
+            us_render: the reference driver's acquisition + beamforming + envelope + log compression (USMain.py:92-224) as one
+            library call at the driver's own sizes, in delay-and-sum terms per second
   cpu_baseline / --impl reference: the C restatement of the reference path (oracle/, kind "port": the real reference needs
             mitsuba/drjit, not installable here) on all host threads.  --impl reference traces the SAME job per step as the
             GPU arm (same `config`); cpu_baseline inside the GPU arm is a bounded ~10 s sample of it.
@@ -514,6 +516,47 @@ def cpu_pt_baseline(args, workload):
             "sample": f"{what}, oracle f32, {threads} threads, {dt:.1f} s"}
 
 
+def usrender_entry(cpu_seconds: float):
+    """SURVEY 8(f) rank 1, the driver's us_render() (USMain.py:92-224) at ITS sizes -- 5 angles x 64 elements x 10 000 samples
+    onto 1040 x 638 pixels -- as one library call (UltraIntegrator.render_bmode -> prt_us_render: acquisition, delay-and-sum,
+    envelope, log compression; only the display image leaves the device).  value = delay-and-sum terms (pixel x angle x
+    element) per second of DEVICE time of the whole call; cpu = the numpy restatement of the beamformer (oracle/pyref.py) on a
+    bounded column sample, one thread."""
+    from prt_b200 import mi_compat as mi, scenes
+    d = scenes.usmain_scene_dict()
+    scene = mi.load_dict(d)
+    integ = scene.integrator()
+    lam = integ.sound_speed / integ.frequency
+    x = np.arange(-0.04, 0.04 + lam / 4, lam / 4)
+    z = np.arange(0.001, 0.05 + lam / 4, lam / 4)
+    terms = x.size * z.size * integ.n_angles * integ.n_elements
+    dev_ms, wall_ms = [], []
+    img = None
+    for it in range(13):
+        t0 = time.perf_counter()
+        img = integ.render_bmode(scene, x, z, dynamic_range=60.0)
+        wall = (time.perf_counter() - t0) * 1e3
+        if it >= 3:
+            dev_ms.append(integ.last_stats["kernel_ms"])
+            wall_ms.append(wall)
+    ms = float(np.median(dev_ms))
+    r = lambda v, n=4: float(f"{v:.{n}g}")
+    out = {"value": r(terms / (ms * 1e-3) / 1e9), "unit": "Gterms/s", "ms": r(ms), "wall_ms": r(float(np.median(wall_ms))),
+           "px": [int(x.size), int(z.size)], "ck": r(float(np.asarray(img, dtype=np.float64).mean()), 3), "n": 1,
+           "kernel": "k_acquire+k_das+k_envelope+k_bmode"}
+    if cpu_seconds > 0:
+        import pyref
+        integ.simulate_acquisition_parallel(scene)
+        ch = np.asarray(integ.channel_buf, dtype=np.float64)
+        cols = 16
+        t0 = time.perf_counter()
+        pyref.das_beamform(ch, integ.angles.numpy(), x[:cols], z, integ.fs, integ.sound_speed, integ.pitch, 0.0, 1.0)
+        dt = time.perf_counter() - t0
+        out["cpu"] = r(cols * z.size * integ.n_angles * integ.n_elements / dt / 1e9)
+        out["cpu_cores"] = 1
+    return out
+
+
 def compact(line):
     """An `also` entry: what the driver's 1 500-character tail has room for."""
     r = lambda x, n=4: None if x is None else float(f"{x:.{n}g}")
@@ -628,6 +671,11 @@ def main():
                 if rank == 0:
                     entries[wl] = {"error": f"{type(ex).__name__}: {ex}"[:160]}
             torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and entries and not args.no_also:
+        try:          # the reference driver's other hot loop (beamforming), one GPU: SURVEY 8(f) rank 1
+            entries["us_render"] = usrender_entry(cpu_s)
+        except Exception as ex:
+            entries["us_render"] = {"error": f"{type(ex).__name__}: {ex}"[:160]}
     if rank == 0:
         line.pop("kernel_classes", None) if entries else None
         if entries:

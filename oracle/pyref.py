@@ -246,3 +246,31 @@ def pulse_shape(channel, fs, fc, sigma_s, cut=4.0):
     for r in range(flat.shape[0]):
         out[r] = np.convolve(flat[r], h, mode="full")[half:half + flat.shape[1]]
     return out.reshape(ch.shape)
+
+
+def das_beamform(ch, angles_deg, x, z, fs, c, pitch, t0=0.0, f_number=0.0):
+    """Plane-wave delay-and-sum onto the pixel grid x (lateral) by z (depth): what the reference asks ultraspy for
+    (`DelayAndSum.beamform`, /root/reference/USMain.py:175-200; ultraspy itself is not vendored -- restated from its
+    published algorithm: linear interpolation of the channel data at t_tx(angle) + t_rx(element) - t0, optional
+    f-number aperture, mean over the transmit angles).  float64, numpy; the checker of prt_das_beamform and the CPU
+    figure beside bench.py's `us_render` entry."""
+    n_a, n_e, T = ch.shape
+    xe = pitch * (np.arange(n_e) - (n_e - 1) / 2)
+    X, Z = np.meshgrid(x, z, indexing="ij")
+    out = np.zeros_like(X, dtype=np.float64)
+    for a in range(n_a):
+        th = np.deg2rad(angles_deg[a])
+        t_tx = (Z * np.cos(th) + X * np.sin(th)) / c
+        for e in range(n_e):
+            dx = X - xe[e]
+            t = t_tx + np.sqrt(dx * dx + Z * Z) / c - t0
+            s = t * fs
+            i0 = np.floor(s).astype(np.int64)
+            ok = (i0 >= 0) & (i0 + 1 < T)
+            if f_number > 0:
+                ok &= np.abs(dx) * 2 * f_number <= Z
+            i0c = np.clip(i0, 0, T - 2)
+            w = s - i0
+            v = ch[a, e, i0c] * (1 - w) + ch[a, e, i0c + 1] * w
+            out += np.where(ok, v, 0.0)
+    return out / n_a

@@ -12,26 +12,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _das_numpy(ch, angles_deg, x, z, fs, c, pitch, t0, f_number):
-    n_a, n_e, T = ch.shape
-    xe = pitch * (np.arange(n_e) - (n_e - 1) / 2)
-    X, Z = np.meshgrid(x, z, indexing="ij")
-    out = np.zeros_like(X, dtype=np.float64)
-    for a in range(n_a):
-        th = np.deg2rad(angles_deg[a])
-        t_tx = (Z * np.cos(th) + X * np.sin(th)) / c
-        for e in range(n_e):
-            dx = X - xe[e]
-            t = t_tx + np.sqrt(dx * dx + Z * Z) / c - t0
-            s = t * fs
-            i0 = np.floor(s).astype(np.int64)
-            ok = (i0 >= 0) & (i0 + 1 < T)
-            if f_number > 0:
-                ok &= np.abs(dx) * 2 * f_number <= Z
-            i0c = np.clip(i0, 0, T - 2)
-            w = s - i0
-            v = ch[a, e, i0c] * (1 - w) + ch[a, e, i0c + 1] * w
-            out += np.where(ok, v, 0.0)
-    return out / n_a
+    import pyref
+    return pyref.das_beamform(ch, angles_deg, x, z, fs, c, pitch, t0, f_number)
 
 
 def test_das_matches_numpy():
