@@ -325,3 +325,30 @@ def test_pinned_pool_never_hands_out_a_live_buffer():
     assert d.ctypes.data != pa                       # a derived view keeps it busy
     del r
     assert ctx.pinned_array((2, 2), np.float32).ctypes.data == pa
+
+
+def test_das_restatement_focuses_a_point_echo():
+    """oracle/pyref.py::das_beamform (the numpy restatement of what USMain.py:175-200 asks ultraspy for; the checker of
+    prt_das_beamform): channel data holding, per element, one linearly interpolated unit echo at the two-way time of flight
+    of a point scatterer must focus AT that pixel, with the closed-form value sum_e ((1 - w_e)^2 + w_e^2) / n_angles."""
+    import pyref
+    fs, c, pitch, n_e, T = 50e6, 1540.0, 3e-4, 16, 2000
+    x0, z0 = 0.0006, 0.0100
+    xe = pitch * (np.arange(n_e) - (n_e - 1) / 2)
+    ch = np.zeros((1, n_e, T))
+    expect = 0.0
+    for e in range(n_e):
+        s = (z0 / c + np.sqrt((x0 - xe[e]) ** 2 + z0 ** 2) / c) * fs
+        i0, w = int(np.floor(s)), s - np.floor(s)
+        ch[0, e, i0], ch[0, e, i0 + 1] = 1 - w, w
+        expect += (1 - w) ** 2 + w ** 2
+    x = x0 + 1e-4 * np.arange(-6, 7)
+    z = z0 + 5e-5 * np.arange(-10, 11)
+    img = pyref.das_beamform(ch, np.array([0.0]), x, z, fs, c, pitch, 0.0, 0.0)
+    ix, iz = np.unravel_index(np.argmax(img), img.shape)
+    assert (ix, iz) == (6, 10)
+    assert abs(img[6, 10] - expect) < 1e-9
+    # an f-number that excludes the outer elements lowers the focus value by exactly their terms
+    img2 = pyref.das_beamform(ch, np.array([0.0]), x, z, fs, c, pitch, 0.0, 4.0)
+    keep = np.abs(x0 - xe) * 2 * 4.0 <= z0
+    assert 0 < keep.sum() < n_e and img2[6, 10] < img[6, 10]
